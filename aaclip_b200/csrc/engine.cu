@@ -1,0 +1,513 @@
+// Context, weight packing and the forward schedules behind the C ABI (include/aaclip_b200.h).
+//
+//   aaclip_visual_forward  == AdaptedCLIP.forward            (model/adapter.py:67-112)
+//   aaclip_forward_fused   == AdaptedCLIP.forward + 4x calculate_similarity_map + level sum + image score
+//                             (test.py:80-93), seg tokens never materialised
+//   aaclip_text_forward    == AdaptedCLIP.encode_text(adapt_text=True)   (model/adapter.py:114-145)
+//
+// Data layout in HBM (per context, sized for cfg.max_batch images; larger batches are processed in chunks):
+//   x     fp32 [B*L, width]      residual stream, token-major (row = b*L + l, l = 0 is the class token)
+//   xn    bf16 [B*L, width]      LayerNorm output / bf16 copy of x: the A operand of the next GEMM
+//   qkv   bf16 [B*L, 3*width]    fused in_proj output, read by the attention kernel through TMA
+//   att   bf16 [B*L, width]      attention output (heads concatenated)
+//   h     bf16 [B*L, mlp_width]  GELU(c_fc) output
+//   a     fp32 [B*L, width]      adapter branch before the norm-matching mix
+//   tap   bf16 [B*P, width]      ln_post(x[:, 1:]) of the current level
+//   s     fp32 [B*P, 2*E]        seg (and, on the last level, det) projection before normalisation
+//   weights: GEMM operands bf16 [out, in] (nn.Linear layout, K contiguous); LN params, biases, embeddings fp32.
+#include <limits.h>
+#include <stdarg.h>
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "internal.h"
+#include "ptx.cuh"
+#include "../../include/aaclip_b200.h"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__global__ void cast_pad_kernel(const float* __restrict__ src, int rows, int cols, bf16* __restrict__ dst, int ld) {
+  const long long total = (long long)rows * ld;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int c = int(t % ld);
+    const long long r = t / ld;
+    dst[t] = __float2bfloat16(c < cols ? src[r * cols + c] : 0.f);
+  }
+}
+
+// x[n*ctx + t, :] = token_embedding[tokens[n, t]] + positional_embedding[t]     (model/adapter.py:118-122)
+__global__ void text_embed_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ emb,
+                                  const float* __restrict__ pos, int ctx, int width, int vocab, float* __restrict__ x) {
+  const int row = blockIdx.x;
+  const int t = row % ctx;
+  int tok = tokens[row];
+  tok = min(max(tok, 0), vocab - 1);
+  const float4* e = reinterpret_cast<const float4*>(emb + (size_t)tok * width);
+  const float4* p = reinterpret_cast<const float4*>(pos + (size_t)t * width);
+  float4* o = reinterpret_cast<float4*>(x + (size_t)row * width);
+  for (int c = threadIdx.x; c < width / 4; c += blockDim.x) {
+    const float4 a = e[c], b = p[c];
+    o[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// gathered[n, :] = x[n*ctx + argmax_t tokens[n, t], :]   (EOT token = highest id, first occurrence; adapter.py:140)
+__global__ void eot_gather_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ x, int ctx, int width,
+                                  float* __restrict__ gathered) {
+  const int n = blockIdx.x;
+  __shared__ int best_t;
+  if (threadIdx.x < 32) {
+    int bv = INT_MIN, bt = 0;
+    for (int t = threadIdx.x; t < ctx; t += 32) {
+      const int v = tokens[n * ctx + t];
+      if (v > bv) { bv = v; bt = t; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ov = __shfl_xor_sync(0xffffffffu, bv, o), ot = __shfl_xor_sync(0xffffffffu, bt, o);
+      if (ov > bv || (ov == bv && ot < bt)) { bv = ov; bt = ot; }
+    }
+    if (threadIdx.x == 0) best_t = bt;
+  }
+  __syncthreads();
+  const float* src = x + ((size_t)n * ctx + best_t) * width;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) gathered[(size_t)n * width + c] = src[c];
+}
+
+struct LayerW {
+  bf16 *qkv_w = nullptr, *out_w = nullptr, *fc_w = nullptr, *proj_w = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *qkv_b = nullptr, *out_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr,
+        *fc_b = nullptr, *proj_b = nullptr;
+};
+
+struct Tower {
+  int width = 0, heads = 0, layers = 0, mlp = 0;
+  std::vector<LayerW> lw;
+  std::vector<bf16*> adapters;
+};
+
+}  // namespace
+
+struct aaclip_ctx {
+  aaclip_cfg cfg;
+  int device = 0;
+  int G = 0, P = 0, L = 0, Kpad = 0, E = 0;
+  int cta_group = 2;
+  long long bytes = 0;
+  long long launches = 0;
+  std::vector<void*> allocs;
+  // visual
+  Tower v;
+  bf16* conv_w = nullptr;
+  float *cls = nullptr, *pos = nullptr, *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr,
+        *ln_post_b = nullptr;
+  std::vector<bf16*> segdet_w;  // per level [E, width]; last level [2E, width] (det_proj appended)
+  // text
+  Tower t;
+  float *tok_emb = nullptr, *t_pos = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr;
+  bf16* t_final = nullptr;
+  // workspaces
+  int cap_rows = 0;  // rows of the token-major buffers
+  float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr;
+  bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *col = nullptr, *tap = nullptr;
+  float *dev_anchors = nullptr, *dev_maps = nullptr, *dev_scores = nullptr, *dev_image = nullptr;  // *_host entry
+  long long stage_cap = 0;
+  cudaStream_t own_stream = nullptr;
+
+  template <typename T>
+  int alloc(T** p, long long n) {
+    void* q = nullptr;
+    const long long nb = std::max<long long>(n, 1) * (long long)sizeof(T);
+    AACLIP_CUDA_CHECK(cudaMalloc(&q, nb));
+    AACLIP_CUDA_CHECK(cudaMemset(q, 0, nb));
+    allocs.push_back(q);
+    bytes += nb;
+    *p = static_cast<T*>(q);
+    return host::OK;
+  }
+};
+
+namespace {
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+int alloc_tower(aaclip_ctx* c, Tower& t, int n_adapters) {
+  const long long w = t.width, ff = t.mlp;
+  t.lw.resize(t.layers);
+  for (auto& l : t.lw) {
+    TRY(c->alloc(&l.qkv_w, 3 * w * w)); TRY(c->alloc(&l.out_w, w * w));
+    TRY(c->alloc(&l.fc_w, ff * w)); TRY(c->alloc(&l.proj_w, w * ff));
+    TRY(c->alloc(&l.ln1_g, w)); TRY(c->alloc(&l.ln1_b, w)); TRY(c->alloc(&l.qkv_b, 3 * w));
+    TRY(c->alloc(&l.out_b, w)); TRY(c->alloc(&l.ln2_g, w)); TRY(c->alloc(&l.ln2_b, w));
+    TRY(c->alloc(&l.fc_b, ff)); TRY(c->alloc(&l.proj_b, w));
+  }
+  t.adapters.resize(n_adapters);
+  for (auto& p : t.adapters) TRY(c->alloc(&p, w * w));
+  return host::OK;
+}
+
+// One transformer block (+ optional adapter mix) over `rows` token rows of width t.width.
+// xn_ready: xn already holds ln_1(x) (written by the previous block's fused adapter mix).
+int run_block(aaclip_ctx* c, const Tower& t, int i, int B, int L, int causal, float adapt_w, bool* xn_ready,
+              cudaStream_t st) {
+  const LayerW& l = t.lw[i];
+  const int rows = B * L, w = t.width, ff = t.mlp;
+  const int cg = c->cta_group;
+  const float eps = 1e-5f;
+  if (!*xn_ready) {
+    TRY(k::launch_layernorm(c->x, l.ln1_g, l.ln1_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st)); c->launches++;
+  }
+  *xn_ready = false;
+  TRY(k::launch_gemm(c->xn, w, l.qkv_w, w, rows, 3 * w, w, l.qkv_b, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
+                     nullptr, 0, cg, st)); c->launches++;
+  TRY(k::launch_attention(c->qkv, c->att, B, L, t.heads, causal, st)); c->launches++;
+  TRY(k::launch_gemm(c->att, w, l.out_w, w, rows, w, w, l.out_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
+                     nullptr, 0, cg, st)); c->launches++;
+  TRY(k::launch_layernorm(c->x, l.ln2_g, l.ln2_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st)); c->launches++;
+  TRY(k::launch_gemm(c->xn, w, l.fc_w, w, rows, ff, w, l.fc_b, c->h, ff, c->cfg.act, gemm::OUT_BF16, nullptr, 0, cg,
+                     st)); c->launches++;
+  TRY(k::launch_gemm(c->h, ff, l.proj_w, ff, rows, w, ff, l.proj_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
+                     nullptr, 0, cg, st)); c->launches++;
+  if (i < (int)t.adapters.size()) {
+    // adapter branch (model/adapter.py:92-99): a = LeakyReLU(x W_a^T); x <- w a |x|/|a| + (1-w) x
+    TRY(k::launch_cast_bf16(c->x, c->xn, (long long)rows * w, st)); c->launches++;
+    TRY(k::launch_gemm(c->xn, w, t.adapters[i], w, rows, w, w, nullptr, c->a, w, gemm::ACT_LEAKY, gemm::OUT_F32,
+                       nullptr, 0, cg, st)); c->launches++;
+    const bool fuse_ln = (i + 1 < t.layers);
+    TRY(k::launch_adapter_mix(c->x, c->a, adapt_w, rows, w, fuse_ln ? t.lw[i + 1].ln1_g : nullptr,
+                              fuse_ln ? t.lw[i + 1].ln1_b : nullptr, eps, fuse_ln ? c->xn : nullptr, st));
+    c->launches++;
+    *xn_ready = fuse_ln;
+  }
+  return host::OK;
+}
+
+// seg_out[level] (fp32 [B,P,E], optional), det_out (fp32 [B,E], optional), dots (optional, [levels][B*P][2] with
+// anchors) for one chunk of B <= max_batch images.
+int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out, long long seg_off, float* det_out,
+                 const float* anchors, float* dots, cudaStream_t st) {
+  const aaclip_cfg& cfg = c->cfg;
+  const int w = cfg.width, L = c->L, P = c->P, E = c->E, rows = B * L, prow = B * P;
+  const int cg = c->cta_group;
+  // stem: conv1 as im2col GEMM, +pos, class token, ln_pre (model/adapter.py:68-85)
+  TRY(k::launch_im2col(image, B, cfg.image_size, cfg.patch_size, c->Kpad, c->col, st)); c->launches++;
+  TRY(k::launch_gemm(c->col, c->Kpad, c->conv_w, c->Kpad, prow, w, c->Kpad, nullptr, c->x, w, gemm::ACT_NONE,
+                     gemm::OUT_F32_PATCH, c->pos, P, cg, st)); c->launches++;
+  TRY(k::launch_cls_rows(c->x, c->cls, c->pos, B, L, w, st)); c->launches++;
+  TRY(k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, nullptr, c->x, st)); c->launches++;
+  bool xn_ready = false;
+  int level = 0;
+  for (int i = 0; i < cfg.layers; ++i) {
+    TRY(run_block(c, c->v, i, B, L, 0, cfg.image_adapt_weight, &xn_ready, st));
+    if (level < cfg.n_levels && cfg.levels[level] == i + 1) {
+      const bool last = (level == cfg.n_levels - 1);
+      // tap: x[:, 1:, :] -> ln_post -> seg_proj (and det_proj on the last tap)   (model/adapter.py:100-111)
+      TRY(k::launch_layernorm(c->x, c->ln_post_g, c->ln_post_b, 1e-5f, prow, w, P, 1, (long long)L * w, c->tap,
+                              nullptr, st)); c->launches++;
+      const bool want_det = last && (det_out != nullptr);
+      const int n_out = want_det ? 2 * E : E;
+      TRY(k::launch_gemm(c->tap, w, c->segdet_w[level], w, prow, n_out, w, nullptr, c->s, 2 * E,
+                         cfg.proj_relu ? gemm::ACT_LEAKY : gemm::ACT_NONE, gemm::OUT_F32, nullptr, 0, cg, st));
+      c->launches++;
+      float* so = (seg_out && seg_out[level]) ? seg_out[level] + seg_off : nullptr;
+      float* dl = dots ? dots + (size_t)level * prow * 2 : nullptr;
+      if (so || dl) {
+        TRY(k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
+        c->launches++;
+      }
+      if (want_det) { TRY(k::launch_det_mean(c->s, 2 * E, E, B, P, E, det_out, st)); c->launches++; }
+      ++level;
+    }
+  }
+  return host::OK;
+}
+
+int check_ready(const aaclip_ctx* c) {
+  if (!c) return host::fail(host::ERR_INVALID, "null context");
+  return host::OK;
+}
+
+}  // namespace
+
+extern "C" const char* aaclip_last_error(void) { return host::last_error().c_str(); }
+extern "C" int aaclip_abi_version(void) { return 1; }
+
+extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device) {
+  if (!out || !cfg) return host::fail(host::ERR_INVALID, "aaclip_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return host::fail(host::ERR_NO_DEVICE, "no CUDA device: aaclip_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return host::fail(host::ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  AACLIP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return host::fail(host::ERR_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major,
+                      prop.minor);
+  if (cfg->width <= 0 || cfg->heads <= 0 || cfg->width != cfg->heads * 64)
+    return host::fail(host::ERR_INVALID, "width %d must equal heads %d * 64", cfg->width, cfg->heads);
+  if (cfg->width % 256 != 0 || cfg->mlp_width % 256 != 0 || cfg->embed_dim % 256 != 0)
+    return host::fail(host::ERR_INVALID, "width / mlp_width / embed_dim must be multiples of 256");
+  if (cfg->patch_size <= 0 || cfg->image_size % cfg->patch_size != 0)
+    return host::fail(host::ERR_INVALID, "image_size %d not divisible by patch_size %d", cfg->image_size, cfg->patch_size);
+  if (cfg->n_levels < 1 || cfg->n_levels > 8) return host::fail(host::ERR_INVALID, "n_levels %d", cfg->n_levels);
+  for (int i = 0; i < cfg->n_levels; ++i)
+    if (cfg->levels[i] < 1 || cfg->levels[i] > cfg->layers || (i > 0 && cfg->levels[i] <= cfg->levels[i - 1]))
+      return host::fail(host::ERR_INVALID, "levels must be strictly ascending within [1, layers]");
+  if (cfg->image_adapt_until < 0 || cfg->image_adapt_until > cfg->layers)
+    return host::fail(host::ERR_INVALID, "image_adapt_until %d", cfg->image_adapt_until);
+  if (cfg->act != AACLIP_ACT_GELU_ERF && cfg->act != AACLIP_ACT_QUICK_GELU)
+    return host::fail(host::ERR_INVALID, "act must be GELU_ERF or QUICK_GELU");
+  if (cfg->max_batch < 1) return host::fail(host::ERR_INVALID, "max_batch %d", cfg->max_batch);
+  if (cfg->t_layers > 0 && (cfg->t_width != cfg->t_heads * 64 || cfg->t_width % 256 != 0 || cfg->t_context < 1 ||
+                            cfg->t_vocab < 1 || cfg->text_adapt_until < 0 || cfg->text_adapt_until > cfg->t_layers))
+    return host::fail(host::ERR_INVALID, "text tower config invalid");
+
+  AACLIP_CUDA_CHECK(cudaSetDevice(device));
+  aaclip_ctx* c = new aaclip_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  c->cta_group = (cfg->cta_group == 1 || cfg->cta_group == 2) ? cfg->cta_group : 2;
+  c->G = cfg->image_size / cfg->patch_size;
+  c->P = c->G * c->G;
+  c->L = c->P + 1;
+  c->E = cfg->embed_dim;
+  const int K = 3 * cfg->patch_size * cfg->patch_size;
+  c->Kpad = (K + 63) / 64 * 64;
+  const long long w = cfg->width, E = c->E;
+
+  int rc = host::OK;
+  auto A = [&](int r) { if (rc == host::OK) rc = r; };
+  c->v.width = cfg->width; c->v.heads = cfg->heads; c->v.layers = cfg->layers; c->v.mlp = cfg->mlp_width;
+  A(alloc_tower(c, c->v, cfg->image_adapt_until));
+  A(c->alloc(&c->conv_w, w * c->Kpad)); A(c->alloc(&c->cls, w)); A(c->alloc(&c->pos, (long long)c->L * w));
+  A(c->alloc(&c->ln_pre_g, w)); A(c->alloc(&c->ln_pre_b, w)); A(c->alloc(&c->ln_post_g, w)); A(c->alloc(&c->ln_post_b, w));
+  c->segdet_w.resize(cfg->n_levels);
+  for (int i = 0; i < cfg->n_levels; ++i) A(c->alloc(&c->segdet_w[i], (i == cfg->n_levels - 1 ? 2 : 1) * E * w));
+  long long max_w = w, max_ff = cfg->mlp_width;
+  long long rows = (long long)cfg->max_batch * c->L;
+  if (cfg->t_layers > 0) {
+    const long long tw = cfg->t_width;
+    c->t.width = cfg->t_width; c->t.heads = cfg->t_heads; c->t.layers = cfg->t_layers; c->t.mlp = 4 * cfg->t_width;
+    A(alloc_tower(c, c->t, cfg->text_adapt_until));
+    A(c->alloc(&c->tok_emb, (long long)cfg->t_vocab * tw)); A(c->alloc(&c->t_pos, (long long)cfg->t_context * tw));
+    A(c->alloc(&c->ln_final_g, tw)); A(c->alloc(&c->ln_final_b, tw)); A(c->alloc(&c->t_final, tw * tw));
+    max_w = std::max(max_w, tw); max_ff = std::max(max_ff, 4 * tw);
+    rows = std::max(rows, (long long)std::max(cfg->max_text, 1) * cfg->t_context);
+  }
+  c->cap_rows = (int)rows;
+  const long long prow = (long long)cfg->max_batch * c->P;
+  A(c->alloc(&c->x, rows * max_w)); A(c->alloc(&c->a, rows * max_w)); A(c->alloc(&c->xn, rows * max_w));
+  A(c->alloc(&c->qkv, rows * 3 * max_w)); A(c->alloc(&c->att, rows * max_w)); A(c->alloc(&c->h, rows * max_ff));
+  A(c->alloc(&c->col, prow * c->Kpad)); A(c->alloc(&c->tap, prow * w)); A(c->alloc(&c->s, prow * 2 * E));
+  A(c->alloc(&c->dots, (long long)cfg->n_levels * prow * 2)); A(c->alloc(&c->det, (long long)cfg->max_batch * E));
+  if (rc != host::OK) { aaclip_destroy(c); return rc; }
+  *out = c;
+  return host::OK;
+}
+
+extern "C" void aaclip_destroy(aaclip_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->stage) cudaFree(c->stage);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" long long aaclip_device_bytes(const aaclip_ctx* c) { return c ? c->bytes : 0; }
+extern "C" long long aaclip_launch_count(const aaclip_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int aaclip_set_weight(aaclip_ctx* c, int id, int layer, const float* src, long long numel, int src_is_host,
+                                 void* stream_) {
+  TRY(check_ready(c));
+  if (!src || numel <= 0) return host::fail(host::ERR_INVALID, "set_weight: empty source");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const aaclip_cfg& cfg = c->cfg;
+  const long long w = cfg.width, ff = cfg.mlp_width, E = c->E, tw = cfg.t_width, tff = 4 * tw;
+  void* dst = nullptr;
+  long long expect = 0;
+  bool to_bf16 = false;
+  int pad_rows = 0, pad_cols = 0, pad_ld = 0;  // conv1 only
+  const bool is_t = (id >= 40);
+  Tower& T = is_t ? c->t : c->v;
+  auto layer_ok = [&](int n) { return layer >= 0 && layer < n; };
+#define PER_LAYER(FIELD, N, BF)                                                          \
+  {                                                                                      \
+    if (!layer_ok(T.layers)) return host::fail(host::ERR_INVALID, "set_weight: layer %d", layer); \
+    dst = T.lw[layer].FIELD; expect = (N); to_bf16 = (BF);                               \
+  }
+  const long long W_ = is_t ? tw : w, FF_ = is_t ? tff : ff;
+  switch (id) {
+    case AACLIP_W_V_CONV1:
+      dst = c->conv_w; expect = w * 3 * cfg.patch_size * cfg.patch_size; to_bf16 = true;
+      pad_rows = (int)w; pad_cols = 3 * cfg.patch_size * cfg.patch_size; pad_ld = c->Kpad; break;
+    case AACLIP_W_V_CLS: dst = c->cls; expect = w; break;
+    case AACLIP_W_V_POS: dst = c->pos; expect = (long long)c->L * w; break;
+    case AACLIP_W_V_LN_PRE_G: dst = c->ln_pre_g; expect = w; break;
+    case AACLIP_W_V_LN_PRE_B: dst = c->ln_pre_b; expect = w; break;
+    case AACLIP_W_V_LN_POST_G: dst = c->ln_post_g; expect = w; break;
+    case AACLIP_W_V_LN_POST_B: dst = c->ln_post_b; expect = w; break;
+    case AACLIP_W_V_LN1_G: case AACLIP_W_T_LN1_G: PER_LAYER(ln1_g, W_, false) break;
+    case AACLIP_W_V_LN1_B: case AACLIP_W_T_LN1_B: PER_LAYER(ln1_b, W_, false) break;
+    case AACLIP_W_V_QKV_W: case AACLIP_W_T_QKV_W: PER_LAYER(qkv_w, 3 * W_ * W_, true) break;
+    case AACLIP_W_V_QKV_B: case AACLIP_W_T_QKV_B: PER_LAYER(qkv_b, 3 * W_, false) break;
+    case AACLIP_W_V_OUT_W: case AACLIP_W_T_OUT_W: PER_LAYER(out_w, W_ * W_, true) break;
+    case AACLIP_W_V_OUT_B: case AACLIP_W_T_OUT_B: PER_LAYER(out_b, W_, false) break;
+    case AACLIP_W_V_LN2_G: case AACLIP_W_T_LN2_G: PER_LAYER(ln2_g, W_, false) break;
+    case AACLIP_W_V_LN2_B: case AACLIP_W_T_LN2_B: PER_LAYER(ln2_b, W_, false) break;
+    case AACLIP_W_V_FC_W: case AACLIP_W_T_FC_W: PER_LAYER(fc_w, FF_ * W_, true) break;
+    case AACLIP_W_V_FC_B: case AACLIP_W_T_FC_B: PER_LAYER(fc_b, FF_, false) break;
+    case AACLIP_W_V_PROJ_W: case AACLIP_W_T_PROJ_W: PER_LAYER(proj_w, W_ * FF_, true) break;
+    case AACLIP_W_V_PROJ_B: case AACLIP_W_T_PROJ_B: PER_LAYER(proj_b, W_, false) break;
+    case AACLIP_W_I_ADAPTER: case AACLIP_W_T_ADAPTER:
+      if (!layer_ok((int)T.adapters.size())) return host::fail(host::ERR_INVALID, "set_weight: adapter %d", layer);
+      dst = T.adapters[layer]; expect = W_ * W_; to_bf16 = true; break;
+    case AACLIP_W_I_SEG_PROJ:
+      if (!layer_ok(cfg.n_levels)) return host::fail(host::ERR_INVALID, "set_weight: level %d", layer);
+      dst = c->segdet_w[layer]; expect = E * w; to_bf16 = true; break;
+    case AACLIP_W_I_DET_PROJ:
+      dst = c->segdet_w[cfg.n_levels - 1] + E * w; expect = E * w; to_bf16 = true; break;
+    case AACLIP_W_T_TOKEN_EMB: dst = c->tok_emb; expect = (long long)cfg.t_vocab * tw; break;
+    case AACLIP_W_T_POS: dst = c->t_pos; expect = (long long)cfg.t_context * tw; break;
+    case AACLIP_W_T_LN_FINAL_G: dst = c->ln_final_g; expect = tw; break;
+    case AACLIP_W_T_LN_FINAL_B: dst = c->ln_final_b; expect = tw; break;
+    case AACLIP_W_T_FINAL_PROJ: dst = c->t_final; expect = tw * tw; to_bf16 = true; break;
+    default: return host::fail(host::ERR_INVALID, "set_weight: unknown weight id %d", id);
+  }
+#undef PER_LAYER
+  if (is_t && cfg.t_layers <= 0) return host::fail(host::ERR_STATE, "set_weight: context has no text tower");
+  if (dst == nullptr) return host::fail(host::ERR_STATE, "set_weight: tensor %d not allocated", id);
+  if (numel != expect)
+    return host::fail(host::ERR_INVALID, "set_weight: id %d layer %d expects %lld values, got %lld", id, layer, expect, numel);
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  const float* dsrc = src;
+  if (src_is_host) {
+    if (c->stage_cap < numel) {
+      AACLIP_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (c->stage) cudaFree(c->stage);
+      c->stage = nullptr;
+      AACLIP_CUDA_CHECK(cudaMalloc(&c->stage, numel * sizeof(float)));
+      c->stage_cap = numel;
+    }
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(c->stage, src, numel * sizeof(float), cudaMemcpyHostToDevice, st));
+    dsrc = c->stage;
+  }
+  if (!to_bf16) {
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(dst, dsrc, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else if (pad_ld) {
+    cast_pad_kernel<<<1024, 256, 0, st>>>(dsrc, pad_rows, pad_cols, static_cast<bf16*>(dst), pad_ld);
+    AACLIP_CUDA_CHECK(cudaGetLastError());
+  } else {
+    cast_pad_kernel<<<1024, 256, 0, st>>>(dsrc, 1, (int)std::min<long long>(numel, INT_MAX), static_cast<bf16*>(dst),
+                                          (int)std::min<long long>(numel, INT_MAX));
+    AACLIP_CUDA_CHECK(cudaGetLastError());
+  }
+  if (src_is_host) AACLIP_CUDA_CHECK(cudaStreamSynchronize(st));  // staging buffer is reused by the next call
+  return host::OK;
+}
+
+extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, float* const* seg_out, float* det_out,
+                                     void* stream_) {
+  TRY(check_ready(c));
+  if (B < 0 || (B > 0 && !image)) return host::fail(host::ERR_INVALID, "visual_forward: B=%d image=%p", B, (const void*)image);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  const long long img_elems = 3LL * c->cfg.image_size * c->cfg.image_size;
+  for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+    const int nb = std::min(c->cfg.max_batch, B - b0);
+    TRY(visual_chunk(c, image + b0 * img_elems, nb, seg_out, (long long)b0 * c->P * c->E,
+                     det_out ? det_out + (long long)b0 * c->E : nullptr, nullptr, nullptr, st));
+  }
+  return host::OK;
+}
+
+extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, const float* anchors, int mode,
+                                    float* maps_out, float* scores_out, void* stream_) {
+  TRY(check_ready(c));
+  if (B < 0 || (B > 0 && (!image || !anchors)))
+    return host::fail(host::ERR_INVALID, "forward_fused: null argument");
+  if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
+    return host::fail(host::ERR_INVALID, "forward_fused: only the test modes are fused (mode=%d)", mode);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  const int S = c->cfg.image_size;
+  const long long img_elems = 3LL * S * S;
+  for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+    const int nb = std::min(c->cfg.max_batch, B - b0);
+    TRY(visual_chunk(c, image + b0 * img_elems, nb, nullptr, 0, c->det, anchors, c->dots, st));
+    if (maps_out) {
+      TRY(k::launch_head_maps(c->dots, nb, c->G, S, mode, c->cfg.n_levels, maps_out + (long long)b0 * S * S, st));
+      c->launches++;
+    }
+    if (scores_out) { TRY(k::launch_scores(c->det, anchors, 0, nb, c->E, scores_out + b0, st)); c->launches++; }
+  }
+  return host::OK;
+}
+
+extern "C" int aaclip_forward_fused_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors,
+                                         int mode, float* host_maps_out, float* host_scores_out) {
+  TRY(check_ready(c));
+  if (B <= 0) return host::OK;
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  if (!c->own_stream) AACLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = c->own_stream;
+  const int S = c->cfg.image_size, mb = c->cfg.max_batch;
+  const long long img_elems = 3LL * S * S;
+  if (!c->dev_image) {
+    TRY(c->alloc(&c->dev_image, mb * img_elems)); TRY(c->alloc(&c->dev_maps, (long long)mb * S * S));
+    TRY(c->alloc(&c->dev_scores, mb)); TRY(c->alloc(&c->dev_anchors, 2LL * c->E));
+  }
+  AACLIP_CUDA_CHECK(cudaMemcpyAsync(c->dev_anchors, host_anchors, 2LL * c->E * sizeof(float), cudaMemcpyHostToDevice, st));
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nb = std::min(mb, B - b0);
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(c->dev_image, host_image + b0 * img_elems, nb * img_elems * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+    TRY(aaclip_forward_fused(c, c->dev_image, nb, c->dev_anchors, mode, host_maps_out ? c->dev_maps : nullptr,
+                             host_scores_out ? c->dev_scores : nullptr, st));
+    if (host_maps_out)
+      AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_maps_out + (long long)b0 * S * S, c->dev_maps,
+                                        (long long)nb * S * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_scores_out)
+      AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_scores_out + b0, c->dev_scores, nb * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st));
+  }
+  AACLIP_CUDA_CHECK(cudaStreamSynchronize(st));
+  return host::OK;
+}
+
+extern "C" int aaclip_text_forward(aaclip_ctx* c, const int32_t* tokens, int n, float* out, void* stream_) {
+  TRY(check_ready(c));
+  const aaclip_cfg& cfg = c->cfg;
+  if (cfg.t_layers <= 0) return host::fail(host::ERR_STATE, "text_forward: context has no text tower");
+  if (n < 0 || (n > 0 && (!tokens || !out))) return host::fail(host::ERR_INVALID, "text_forward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  const int ctx = cfg.t_context, tw = cfg.t_width;
+  const int chunk = std::max(1, c->cap_rows / ctx);
+  for (int n0 = 0; n0 < n; n0 += chunk) {
+    const int nn = std::min(chunk, n - n0);
+    const int32_t* tk = tokens + (long long)n0 * ctx;
+    text_embed_kernel<<<nn * ctx, 192, 0, st>>>(tk, c->tok_emb, c->t_pos, ctx, tw, cfg.t_vocab, c->x);
+    AACLIP_CUDA_CHECK(cudaGetLastError()); c->launches++;
+    bool xn_ready = false;
+    for (int i = 0; i < cfg.t_layers; ++i)
+      TRY(run_block(c, c->t, i, nn, ctx, 1, cfg.text_adapt_weight, &xn_ready, st));
+    // ln_final is row-wise, so gather the EOT rows first, then normalise only those (model/adapter.py:138-140)
+    eot_gather_kernel<<<nn, 256, 0, st>>>(tk, c->x, ctx, tw, c->a);
+    AACLIP_CUDA_CHECK(cudaGetLastError()); c->launches++;
+    TRY(k::launch_layernorm(c->a, c->ln_final_g, c->ln_final_b, 1e-5f, nn, tw, 0, 0, 0, c->xn, nullptr, st));
+    c->launches++;
+    TRY(k::launch_gemm(c->xn, tw, c->t_final, tw, nn, tw, tw, nullptr, out + (long long)n0 * tw, tw, gemm::ACT_LEAKY,
+                       gemm::OUT_F32, nullptr, 0, c->cta_group, st)); c->launches++;
+  }
+  return host::OK;
+}

@@ -1,0 +1,281 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:   out = epilogue(A[M,K] . W[N,K]^T)
+//
+//   * A (activations) and W (nn.Linear weight, [out_features, in_features]) are bf16, K contiguous.
+//   * TMA (cp.async.bulk.tensor, 128B swizzle) stages 64-wide K slabs into a multi-stage smem ring.
+//   * One elected thread issues tcgen05.mma (kind::f16, fp32 accumulation) into TMEM; the accumulator
+//     is double buffered (2 x 256 columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
+//   * CG = 1: one CTA computes a 128x256 tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2)
+//     computes a 256x256 tile; each CTA stages its own 128 rows of A and 128 rows of W, halving the
+//     smem/L2 operand traffic per SM.
+//   * 8 epilogue warps read TMEM with tcgen05.ld (lane == output row) and apply the fused epilogue:
+//     bias, erf-GELU / QuickGELU / LeakyReLU, bf16 or fp32 store, in-place fp32 residual add, or the
+//     patch-embedding scatter (+positional embedding).
+//
+// These replace the cuBLAS/cuDNN + ATen elementwise call sites of the reference:
+//   in_proj / out_proj   model/transformer.py:237 (nn.MultiheadAttention)      -> ACT_NONE + OUT_BF16 / OUT_F32_RESID
+//   mlp.c_fc + gelu      model/transformer.py:211-217,257                      -> ACT_GELU_ERF|ACT_QUICK_GELU + OUT_BF16
+//   mlp.c_proj + resid   model/transformer.py:257                              -> OUT_F32_RESID
+//   SimpleAdapter        model/adapter_modules.py:6-13, model/adapter.py:92    -> ACT_LEAKY + OUT_F32
+//   SimpleProj           model/adapter_modules.py:16-26, model/adapter.py:106  -> ACT_NONE|ACT_LEAKY + OUT_F32
+//   conv1 + cls/pos      model/adapter.py:68-82                                -> OUT_F32_PATCH
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace gemm {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_QUICK_GELU = 2, ACT_LEAKY = 3 };
+enum Out : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_RESID = 2, OUT_F32_PATCH = 3 };
+
+struct Args {
+  int M, N, K;
+  const float* bias;  // [N] or nullptr
+  void* out;          // bf16 or f32, row pitch ldo elements
+  int ldo;
+  const float* pos;   // OUT_F32_PATCH: positional embedding [P+1, N]
+  int P;              // OUT_F32_PATCH: patches per image
+};
+
+template <int CG>
+struct Cfg {
+  static constexpr int BM = 128;           // accumulator rows per CTA (== TMEM lanes)
+  static constexpr int BN = 256;           // tile N (per CTA pair when CG == 2)
+  static constexpr int BN_CTA = BN / CG;   // rows of W staged by each CTA
+  static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
+  static constexpr int UMMA_K = 16;
+  static constexpr int STAGES = (CG == 1) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int NUM_EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + NUM_EPI_WARPS * 32;
+  static constexpr int TMEM_COLS = 512;    // 2 accumulator buffers x 256 fp32 columns
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + ~10 FMA, branch free.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);  // 0.5x(1+erf(x/sqrt2)); sign(x)*erf_abs folded into |hx|
+}
+__device__ __forceinline__ float quick_gelu(float x) {
+  return x * __frcp_rn(1.0f + exp2f(-1.702f * 1.4426950408889634f * x));
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (ACT == ACT_GELU_ERF) return gelu_erf(x);
+  else if constexpr (ACT == ACT_QUICK_GELU) return quick_gelu(x);
+  else if constexpr (ACT == ACT_LEAKY) return x > 0.f ? x : 0.01f * x;
+  else return x;
+}
+
+template <int ACT, int OUT>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col, const Args& a) {
+  if (row >= a.M || col >= a.N) return;
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (a.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT>(f[j]);
+
+  if constexpr (OUT == OUT_BF16) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + size_t(row) * a.ldo + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      w.x = ptx::pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+      w.y = ptx::pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+      w.z = ptx::pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+      w.w = ptx::pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+      o[j] = w;
+    }
+  } else {
+    size_t orow = row;
+    if constexpr (OUT == OUT_F32_PATCH) {
+      // patch row m = b*P + p  ->  token row b*(P+1) + 1 + p, plus positional_embedding[1 + p]
+      const int b = row / a.P, p = row - b * a.P;
+      orow = size_t(b) * (a.P + 1) + 1 + p;
+      const float4* p4 = reinterpret_cast<const float4*>(a.pos + size_t(p + 1) * a.N + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q = __ldg(p4 + j);
+        f[4 * j + 0] += q.x; f[4 * j + 1] += q.y; f[4 * j + 2] += q.z; f[4 * j + 3] += q.w;
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + orow * a.ldo + col);
+    if constexpr (OUT == OUT_F32_RESID) {
+      float4 r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = o[j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[4 * j + 0] += r[j].x; f[4 * j + 1] += r[j].y; f[4 * j + 2] += r[j].z; f[4 * j + 3] += r[j].w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j + 0], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  }
+}
+
+template <int CG, int ACT, int OUT>
+__global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args args) {
+  using C = Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  // identical offset in both CTAs of a pair: the dynamic smem window starts at the same address
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t lane = ptx::lane_id();
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+
+  const int tiles_m = (args.M + C::BM * CG - 1) / (C::BM * CG);
+  const int tiles_n = (args.N + C::BN - 1) / C::BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (args.K + C::BK - 1) / C::BK;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && ptx::elect_one()) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full[s], CG);   // leader's arrive.expect_tx (+ the peer producer's remote arrive)
+      ptx::mbar_init(&empty[s], 1);   // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);                          // tcgen05.commit
+      ptx::mbar_init(&tempty[a], CG * C::NUM_EPI_WARPS);     // one arrive per epilogue warp of the pair
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish<CG>();
+  }
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (ptx::elect_one()) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+        const int m0 = m_blk * C::BM * CG + int(cta_rank) * C::BM;
+        const int n0 = n_blk * C::BN + int(cta_rank) * C::BN_CTA;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
+          void* a_dst = sA + s * C::A_BYTES;
+          void* b_dst = sB + s * C::B_BYTES;
+          if constexpr (CG == 1) {
+            ptx::mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+            ptx::tma_load_2d(a_dst, &tmA, &full[s], kb * C::BK, m0);
+            ptx::tma_load_2d(b_dst, &tmB, &full[s], kb * C::BK, n0);
+          } else {
+            if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+            ptx::tma_load_2d_cg2(a_dst, &tmA, &full[s], kb * C::BK, m0);
+            ptx::tma_load_2d_cg2(b_dst, &tmB, &full[s], kb * C::BK, n0);
+            if (!leader) ptx::mbar_arrive_cluster(&full[s], 0);
+          }
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (pair leader only)
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(C::BM * CG, C::BN, 0, 0);
+      int s = 0; uint32_t ph = 0; uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        ptx::mbar_wait(&tempty[acc], aph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + s * C::A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + s * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < C::BK / C::UMMA_K; ++k) {
+            const uint64_t ad = ptx::umma_desc_kmajor_sw128(a_addr + k * C::UMMA_K * 2);
+            const uint64_t bd = ptx::umma_desc_kmajor_sw128(b_addr + k * C::UMMA_K * 2);
+            ptx::mma_f16_ss<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CG == 1) ptx::mma_commit(&empty[s]); else ptx::mma_commit_cg2(&empty[s], 0x3);
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+        if constexpr (CG == 1) ptx::mma_commit(&tfull[acc]); else ptx::mma_commit_cg2(&tfull[acc], 0x3);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: TMEM -> regs -> global
+    const uint32_t q = warp & 3u;            // TMEM lane quarter this warp may read
+    const uint32_t half = (warp - 4u) >> 2;  // which 128 accumulator columns
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      ptx::mbar_wait(&tfull[acc], aph);
+      ptx::tc_fence_after();
+      const int row = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u + lane);
+      const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * C::BN + half * 128u;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (c == 3) {
+          // every TMEM read of this accumulator buffer is done: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) ptx::mbar_arrive(&tempty[acc]); else ptx::mbar_arrive_cluster(&tempty[acc], 0);
+          }
+        }
+        epilogue_chunk<ACT, OUT>(v, row, n_blk * C::BN + int(half) * 128 + c * 32, args);
+      }
+    }
+  }
+
+  // ===================================================== teardown
+  __syncwarp();
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace gemm

@@ -1,0 +1,55 @@
+// Cross-translation-unit launch functions (host side).  Every function enqueues on `stream`, returns
+// host::OK or a negative error code and records a message retrievable by aaclip_last_error().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace k {
+
+// out = epilogue(A[M,K] . W[N,K]^T); A, W bf16 K-contiguous (pitches lda/ldw elements, multiples of 8).
+// act: gemm::Act, out_mode: gemm::Out, cta_group: 1 or 2.
+int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out,
+                int ldo, int act, int out_mode, const float* pos, int P, int cta_group, cudaStream_t stream);
+
+// LayerNorm over the last dim (width % 128 == 0, <= 4096), fp32 in, affine, eps; one warp per row.
+//   rows are read at  x + (r / rows_per_group) * group_stride + (r % rows_per_group + row_offset) * width
+//   (lets ln_post skip the CLS row of every image without a copy).  out_bf16 and/or out_f32 may be null.
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
+                     int rows_per_group, int row_offset, long long group_stride, void* out_bf16, float* out_f32,
+                     cudaStream_t stream);
+
+// fp32 -> bf16 cast of a [rows, width] matrix.
+int launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_t stream);
+
+// AA-CLIP adapter mix (model/adapter.py:92-99): x <- w * a * ||x|| / ||a|| + (1-w) * x, row-wise over `width`.
+// Optionally fuses the next LayerNorm: if ln_gamma != null writes LN(x_new) as bf16 to ln_out.
+int launch_adapter_mix(float* x, const float* a, float w, int rows, int width, const float* ln_gamma,
+                       const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream);
+
+// Row-wise L2 normalise (F.normalize, eps 1e-12) of s[rows, ld] columns [col0, col0+width).
+//   out_f32 / out_bf16: normalised rows [rows, width] (either may be null)
+//   anchors != null ([width, 2] fp32): also dots[r] = (<f_r, T[:,0]>, <f_r, T[:,1]>) as float2
+int launch_l2norm_rows(const float* s, int ld, int col0, int rows, int width, float* out_f32, void* out_bf16,
+                       const float* anchors, float* dots, cudaStream_t stream);
+
+// det token: mean over P patches of the L2-normalised rows of s[b*P + p, col0:col0+width] -> det[b, width]
+int launch_det_mean(const float* s, int ld, int col0, int B, int P, int width, float* det, cudaStream_t stream);
+
+// patch-embedding im2col: image fp32 [B,3,S,S] -> bf16 [B*G*G, Kpad], k = c*ps*ps + i*ps + j, zero padded
+int launch_im2col(const float* image, int B, int S, int ps, int Kpad, void* out_bf16, cudaStream_t stream);
+
+// class-token rows: x[b*L + 0, :] = cls + pos[0]
+int launch_cls_rows(float* x, const float* cls, const float* pos, int B, int L, int width, cudaStream_t stream);
+
+// Multi-head attention, head dim 64, bf16 qkv[M = B*L, 3*width] (q | k | v, heads contiguous 64-wide),
+// out bf16 [M, width].  causal: additive -inf above the diagonal (text tower).  scale = 1/sqrt(64).
+int launch_attention(const void* qkv, void* out, int B, int L, int heads, int causal, cudaStream_t stream);
+
+// Anomaly-map head (forward_utils.py:196-216 + test.py:83-93), see head.cu
+int launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors, int anchors_batched,
+                      int B, int P, int E, float* dots /*[n_levels][B*P][2]*/, cudaStream_t stream);
+int launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_levels, float* maps, cudaStream_t stream);
+int launch_scores(const float* det, const float* anchors, int anchors_batched, int B, int E, float* scores,
+                  cudaStream_t stream);
+
+}  // namespace k

@@ -1,0 +1,320 @@
+// HBM-bound row kernels: one warp per row, 16-byte vectorised coalesced loads, warp-shuffle reductions,
+// fp32 statistics.  They replace ATen's native_layer_norm / linalg_vector_norm / mul / div / add chains:
+//   LayerNorm           model/transformer.py:37-43  (ln_pre, ln_1, ln_2, ln_post, ln_final)
+//   adapter mix         model/adapter.py:93-99
+//   F.normalize / mean  model/adapter.py:109-111
+//   conv1 im2col, cls   model/adapter.py:68-82
+#include <stdarg.h>
+#include <algorithm>
+#include "common.cuh"
+#include "internal.h"
+#include "ptx.cuh"
+#include "../../include/aaclip_b200.h"
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Row of VEC*128 floats held as VEC float4 per lane: element index = (i*32 + lane)*4 + {0..3}.
+template <int VEC>
+__device__ __forceinline__ void load_row(const float* row, int lane, float4 (&v)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = *reinterpret_cast<const float4*>(row + (i * 32 + lane) * 4);
+}
+template <int VEC>
+__device__ __forceinline__ float row_sum(const float4 (&v)[VEC]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  return ptx::warp_sum(s);
+}
+template <int VEC>
+__device__ __forceinline__ float row_sumsq(const float4 (&v)[VEC]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  return ptx::warp_sum(s);
+}
+
+// y = (x - mean) * rstd * gamma + beta written as bf16 (8 B per lane-chunk) and/or fp32
+template <int VEC>
+__device__ __forceinline__ void layernorm_store(const float4 (&v)[VEC], int lane, int width, const float* gamma,
+                                                const float* beta, float eps, __nv_bfloat16* out_bf16,
+                                                float* out_f32) {
+  const float inv_w = 1.0f / float(width);
+  const float mean = row_sum<VEC>(v) * inv_w;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(ptx::warp_sum(ss) * inv_w + eps);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = ldg4(gamma + col), b = ldg4(beta + col);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out_bf16) {
+      uint2 w;
+      w.x = ptx::pack_bf16x2(y.x, y.y);
+      w.y = ptx::pack_bf16x2(y.z, y.w);
+      *reinterpret_cast<uint2*>(out_bf16 + col) = w;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = y;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, int rows, int rows_per_group, int row_offset, long long group_stride,
+                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  constexpr int width = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int g = r / rows_per_group, within = r - g * rows_per_group;
+  const float* src = x + (long long)g * group_stride + (long long)(within + row_offset) * width;
+  float4 v[VEC];
+  load_row<VEC>(src, lane, v);
+  layernorm_store<VEC>(v, lane, width, gamma, beta, eps, out_bf16 ? out_bf16 + (size_t)r * width : nullptr,
+                       out_f32 ? out_f32 + (size_t)r * width : nullptr);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+adapter_mix_kernel(float* __restrict__ x, const float* __restrict__ a, float w, int rows,
+                   const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float eps,
+                   __nv_bfloat16* __restrict__ ln_out) {
+  constexpr int width = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float* xr = x + (size_t)r * width;
+  float4 xv[VEC], av[VEC];
+  load_row<VEC>(xr, lane, xv);
+  load_row<VEC>(a + (size_t)r * width, lane, av);
+  const float nx = sqrtf(row_sumsq<VEC>(xv));
+  const float na = sqrtf(row_sumsq<VEC>(av));
+  const float sa = w * (nx / na);  // no epsilon, as in the reference (model/adapter.py:94-98)
+  const float sx = 1.0f - w;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    xv[i].x = sa * av[i].x + sx * xv[i].x;
+    xv[i].y = sa * av[i].y + sx * xv[i].y;
+    xv[i].z = sa * av[i].z + sx * xv[i].z;
+    xv[i].w = sa * av[i].w + sx * xv[i].w;
+    *reinterpret_cast<float4*>(xr + (i * 32 + lane) * 4) = xv[i];
+  }
+  if (ln_gamma != nullptr)
+    layernorm_store<VEC>(xv, lane, width, ln_gamma, ln_beta, eps, ln_out + (size_t)r * width, nullptr);
+}
+
+// F.normalize(dim=-1, eps=1e-12) of s[r, col0:col0+width]; optionally also the two anchor dot products
+// dots[r] = (<f, T[:,0]>, <f, T[:,1]>) of the normalised row with anchors T [width, 2]  (forward_utils.py:199)
+template <int VEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_kernel(const float* __restrict__ s, int ld, int col0, int rows, float* __restrict__ out_f32,
+                   __nv_bfloat16* __restrict__ out_bf16, const float* __restrict__ anchors,
+                   float* __restrict__ dots) {
+  constexpr int width = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float4 v[VEC];
+  load_row<VEC>(s + (size_t)r * ld + col0, lane, v);
+  const float inv = 1.0f / fmaxf(sqrtf(row_sumsq<VEC>(v)), 1e-12f);
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    float4 y = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)r * width + col) = y;
+    if (out_bf16) {
+      uint2 w;
+      w.x = ptx::pack_bf16x2(y.x, y.y);
+      w.y = ptx::pack_bf16x2(y.z, y.w);
+      *reinterpret_cast<uint2*>(out_bf16 + (size_t)r * width + col) = w;
+    }
+    if (anchors) {
+      const float4 t0 = ldg4(anchors + col * 2), t1 = ldg4(anchors + col * 2 + 4);
+      d0 += (y.x * t0.x + y.y * t0.z) + (y.z * t1.x + y.w * t1.z);
+      d1 += (y.x * t0.y + y.y * t0.w) + (y.z * t1.y + y.w * t1.w);
+    }
+  }
+  if (anchors) {
+    d0 = ptx::warp_sum(d0);
+    d1 = ptx::warp_sum(d1);
+    if (lane == 0) *reinterpret_cast<float2*>(dots + (size_t)r * 2) = make_float2(d0, d1);
+  }
+}
+
+// det[b, :] = mean_p normalize(s[b*P + p, col0:col0+width])      (model/adapter.py:110-111)
+// one block per (image, 128-column slice): phase 1 row inverse norms into smem, phase 2 column means.
+__global__ void __launch_bounds__(256)
+det_mean_kernel(const float* __restrict__ s, int ld, int col0, int P, int width, float* __restrict__ det) {
+  extern __shared__ float inv_norm[];  // [P]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* base = s + (size_t)b * P * ld + col0;
+  for (int p = warp; p < P; p += 8) {
+    const float* row = base + (size_t)p * ld;
+    float ss = 0.f;
+    for (int c = lane * 4; c < width; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    ss = ptx::warp_sum(ss);
+    if (lane == 0) inv_norm[p] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  __syncthreads();
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c < width) {
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) acc += base[(size_t)p * ld + c] * inv_norm[p];
+    det[(size_t)b * width + c] = acc / float(P);
+  }
+}
+
+// image fp32 [B,3,S,S] -> A bf16 [B*G*G, Kpad]; k = c*ps*ps + i*ps + j (conv1.weight.view(width,-1) order)
+__global__ void im2col_kernel(const float* __restrict__ img, int B, int S, int ps, int G, int Kpad,
+                              __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)B * G * G * (Kpad / 2);
+  const int K = 3 * ps * ps;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int kp = int(t % (Kpad / 2));
+    const long long m = t / (Kpad / 2);
+    const int gx = int(m % G), gy = int((m / G) % G), b = int(m / ((long long)G * G));
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = kp * 2 + e;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k / (ps * ps), rem = k - c * ps * ps, i = rem / ps, j = rem - i * ps;
+        val = __ldg(img + (((long long)b * 3 + c) * S + (gy * ps + i)) * S + gx * ps + j);
+      }
+      v[e] = val;
+    }
+    *reinterpret_cast<uint32_t*>(out + m * Kpad + kp * 2) = ptx::pack_bf16x2(v[0], v[1]);
+  }
+}
+
+__global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int B, int L, int width) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) x[(size_t)b * L * width + c] = cls[c] + pos[c];
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4;
+       t += (long long)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + t * 4);
+    uint2 w;
+    w.x = ptx::pack_bf16x2(v.x, v.y);
+    w.y = ptx::pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + t * 4) = w;
+  }
+}
+
+inline int row_blocks(int rows) { return (rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK; }
+
+#define DISPATCH_VEC(width, CALL)                                                              \
+  switch ((width) / 128) {                                                                     \
+    case 1: { constexpr int V = 1; CALL; } break;                                              \
+    case 2: { constexpr int V = 2; CALL; } break;                                              \
+    case 4: { constexpr int V = 4; CALL; } break;                                              \
+    case 6: { constexpr int V = 6; CALL; } break;                                              \
+    case 8: { constexpr int V = 8; CALL; } break;                                              \
+    default: return host::fail(host::ERR_INVALID, "row kernel: unsupported width %d", (width)); \
+  }
+
+}  // namespace
+
+int k::launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
+                        int rows_per_group, int row_offset, long long group_stride, void* out_bf16, float* out_f32,
+                        cudaStream_t stream) {
+  if (rows <= 0) return host::OK;
+  if (width % 128 != 0) return host::fail(host::ERR_INVALID, "layernorm: width %d must be a multiple of 128", width);
+  if (rows_per_group <= 0) { rows_per_group = rows; row_offset = 0; group_stride = 0; }
+  DISPATCH_VEC(width, (layernorm_kernel<V><<<row_blocks(rows), WARPS_PER_BLOCK * 32, 0, stream>>>(
+                          x, gamma, beta, eps, rows, rows_per_group, row_offset, group_stride,
+                          static_cast<__nv_bfloat16*>(out_bf16), out_f32)));
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+int k::launch_adapter_mix(float* x, const float* a, float w, int rows, int width, const float* ln_gamma,
+                          const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream) {
+  if (rows <= 0) return host::OK;
+  if (width % 128 != 0) return host::fail(host::ERR_INVALID, "adapter_mix: width %d must be a multiple of 128", width);
+  DISPATCH_VEC(width, (adapter_mix_kernel<V><<<row_blocks(rows), WARPS_PER_BLOCK * 32, 0, stream>>>(
+                          x, a, w, rows, ln_gamma, ln_beta, eps, static_cast<__nv_bfloat16*>(ln_out_bf16))));
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+int k::launch_l2norm_rows(const float* s, int ld, int col0, int rows, int width, float* out_f32, void* out_bf16,
+                          const float* anchors, float* dots, cudaStream_t stream) {
+  if (rows <= 0) return host::OK;
+  if (width % 128 != 0 || ld % 4 != 0 || col0 % 4 != 0)
+    return host::fail(host::ERR_INVALID, "l2norm: width %d / ld %d / col0 %d alignment", width, ld, col0);
+  DISPATCH_VEC(width, (l2norm_rows_kernel<V><<<row_blocks(rows), WARPS_PER_BLOCK * 32, 0, stream>>>(
+                          s, ld, col0, rows, out_f32, static_cast<__nv_bfloat16*>(out_bf16), anchors, dots)));
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+int k::launch_det_mean(const float* s, int ld, int col0, int B, int P, int width, float* det, cudaStream_t stream) {
+  if (B <= 0) return host::OK;
+  if (width % 4 != 0 || ld % 4 != 0 || col0 % 4 != 0) return host::fail(host::ERR_INVALID, "det_mean: alignment");
+  dim3 grid(B, (width + 255) / 256);
+  det_mean_kernel<<<grid, 256, P * sizeof(float), stream>>>(s, ld, col0, P, width, det);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+int k::launch_im2col(const float* image, int B, int S, int ps, int Kpad, void* out_bf16, cudaStream_t stream) {
+  if (S % ps != 0 || Kpad % 8 != 0 || Kpad < 3 * ps * ps)
+    return host::fail(host::ERR_INVALID, "im2col: S=%d ps=%d Kpad=%d", S, ps, Kpad);
+  const int G = S / ps;
+  const long long total = (long long)B * G * G * (Kpad / 2);
+  const int blocks = int(std::min<long long>((total + 255) / 256, 148LL * 32));
+  im2col_kernel<<<blocks, 256, 0, stream>>>(image, B, S, ps, G, Kpad, static_cast<__nv_bfloat16*>(out_bf16));
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+int k::launch_cls_rows(float* x, const float* cls, const float* pos, int B, int L, int width, cudaStream_t stream) {
+  cls_rows_kernel<<<B, 256, 0, stream>>>(x, cls, pos, B, L, width);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+int k::launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_t stream) {
+  if (n % 4 != 0) return host::fail(host::ERR_INVALID, "cast_bf16: n %% 4 != 0");
+  const long long n4 = n / 4;
+  const int blocks = int(std::min<long long>((n4 + 255) / 256, 148LL * 16));
+  cast_bf16_kernel<<<blocks, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out_bf16), n4);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
+extern "C" int aaclip_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
+                                void* out_bf16, float* out_f32, void* stream) {
+  return k::launch_layernorm(x, gamma, beta, eps, rows, width, 0, 0, 0, out_bf16, out_f32,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int aaclip_adapter_mix(float* x, const float* a, float w, int rows, int width, void* stream) {
+  return k::launch_adapter_mix(x, a, w, rows, width, nullptr, nullptr, 0.f, nullptr,
+                               static_cast<cudaStream_t>(stream));
+}

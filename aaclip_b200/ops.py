@@ -1,0 +1,120 @@
+"""Torch-tensor front ends of the building-block entry points of the C ABI.
+
+These only validate shapes/dtypes, allocate outputs with torch (device memory + current stream are the
+plumbing torch provides) and pass raw pointers to libaaclip_b200.so.  No arithmetic happens in Python and
+nothing here falls back to a torch implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_LEAKY, ACT_NONE, ACT_QUICK_GELU, HEAD_TEST_INDUSTRIAL, HEAD_TEST_MEDICAL,
+                   HEAD_TRAIN_SOFTMAX, OUT_BF16, OUT_F32, OUT_F32_PATCH, OUT_F32_RESID, check, cur_stream, ptr)
+
+__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head",
+           "ACT_NONE", "ACT_GELU_ERF", "ACT_QUICK_GELU", "ACT_LEAKY",
+           "OUT_BF16", "OUT_F32", "OUT_F32_RESID", "OUT_F32_PATCH",
+           "HEAD_TEST_INDUSTRIAL", "HEAD_TEST_MEDICAL", "HEAD_TRAIN_SOFTMAX"]
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (aaclip_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         out_mode: int = OUT_F32, out: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
+         patches: int = 0, cta_group: int = 2) -> torch.Tensor:
+    """out = epilogue(a[M,K] @ w[N,K]^T) on the tcgen05 GEMM.  a, w bf16; bias/pos fp32."""
+    _need(a, torch.bfloat16, "a"); _need(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise ValueError(f"K mismatch: a {tuple(a.shape)} vs w {tuple(w.shape)}")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    if out_mode == OUT_F32_PATCH:
+        if pos is None or patches <= 0 or out is None:
+            raise ValueError("OUT_F32_PATCH needs pos, patches and a preallocated out")
+        _need(pos, torch.float32, "pos")
+    if out is None:
+        if out_mode == OUT_F32_RESID:
+            raise ValueError("OUT_F32_RESID accumulates into `out`")
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if out_mode == OUT_BF16 else torch.float32)
+    _need(out, torch.bfloat16 if out_mode == OUT_BF16 else torch.float32, "out")
+    lib = _lib.load()
+    check(lib.aaclip_gemm_bf16(ptr(a), K, ptr(w), K, M, N, K, ptr(bias), ptr(out), out.shape[-1], act, out_mode,
+                               ptr(pos), patches, cta_group, cur_stream()))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out_bf16: bool = True, out_f32: bool = False):
+    _need(x, torch.float32, "x"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    rows, width = x.shape
+    ob = torch.empty(rows, width, device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    of = torch.empty_like(x) if out_f32 else None
+    check(_lib.load().aaclip_layernorm(ptr(x), ptr(gamma), ptr(beta), eps, rows, width, ptr(ob), ptr(of),
+                                       cur_stream()))
+    return ob, of
+
+
+def attention(qkv: torch.Tensor, B: int, L: int, heads: int, causal: bool = False) -> torch.Tensor:
+    """qkv bf16 [B*L, 3*heads*64] -> bf16 [B*L, heads*64] = softmax(q k^T / 8 [+ causal mask]) v per head."""
+    _need(qkv, torch.bfloat16, "qkv")
+    if tuple(qkv.shape) != (B * L, 3 * heads * 64):
+        raise ValueError(f"qkv shape {tuple(qkv.shape)} != ({B * L}, {3 * heads * 64})")
+    out = torch.empty(B * L, heads * 64, device=qkv.device, dtype=torch.bfloat16)
+    check(_lib.load().aaclip_attention(ptr(qkv), ptr(out), B, L, heads, int(causal), cur_stream()))
+    return out
+
+
+def adapter_mix(x: torch.Tensor, a: torch.Tensor, w: float) -> torch.Tensor:
+    """In place: x <- w * a * |x| / |a| + (1 - w) * x, norms over the last dim."""
+    _need(x, torch.float32, "x"); _need(a, torch.float32, "a")
+    rows, width = x.shape
+    check(_lib.load().aaclip_adapter_mix(ptr(x), ptr(a), w, rows, width, cur_stream()))
+    return x
+
+
+def anomaly_head(seg: Sequence[torch.Tensor], anchors: torch.Tensor, img_size: int, mode: int,
+                 det: Optional[torch.Tensor] = None, want_maps: bool = True):
+    """seg: list of [B,P,E] (fp32 or bf16) normalised patch tokens; anchors fp32 [E,2] or [B,E,2].
+
+    Returns (maps, scores): test modes maps fp32 [B,S,S] summed over levels; train mode [n_levels,B,2,S,S];
+    scores fp32 [B] if det is given, else None.
+    """
+    n = len(seg)
+    if n == 0:
+        raise ValueError("anomaly_head: no levels")
+    B, P, E = seg[0].shape
+    is_bf16 = seg[0].dtype == torch.bfloat16
+    for t in seg:
+        _need(t, torch.bfloat16 if is_bf16 else torch.float32, "seg level")
+        if tuple(t.shape) != (B, P, E):
+            raise ValueError("all levels must share one shape")
+    _need(anchors, torch.float32, "anchors")
+    batched = anchors.dim() == 3
+    if tuple(anchors.shape) != ((B, E, 2) if batched else (E, 2)):
+        raise ValueError(f"anchors shape {tuple(anchors.shape)}")
+    dev = seg[0].device
+    maps = None
+    if want_maps:
+        shape = (n, B, 2, img_size, img_size) if mode == HEAD_TRAIN_SOFTMAX else (B, img_size, img_size)
+        maps = torch.empty(shape, device=dev, dtype=torch.float32)
+    scores = None
+    if det is not None:
+        _need(det, torch.float32, "det")
+        scores = torch.empty(B, device=dev, dtype=torch.float32)
+    arr = (C.c_void_p * n)(*[t.data_ptr() for t in seg])
+    check(_lib.load().aaclip_anomaly_head(arr, n, int(is_bf16), ptr(anchors), int(batched), ptr(det), B, P, E,
+                                          img_size, mode, ptr(maps), ptr(scores), cur_stream()))
+    return maps, scores

@@ -1,0 +1,172 @@
+/* aaclip_b200 — C ABI of the B200-native AA-CLIP inference hot path.
+ *
+ * The reference (wei-paul/AA-CLIP) has no FFI of its own: the boundary its callers (test.py:get_predictions,
+ * forward_utils.get_adapted_text_embedding) see is the Python surface  AdaptedCLIP.forward / .encode_text
+ * (model/adapter.py:67-145)  and  calculate_similarity_map (forward_utils.py:196-216).  aaclip_b200/ mirrors
+ * that surface in Python and binds THIS library with ctypes (INTEGRATION.md shows the stub); every entry point
+ * below names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *   - unless a parameter is named host_*, pointers are DEVICE pointers owned by the caller; the context
+ *     owns only its packed weights and workspaces.
+ *   - calls enqueue on `stream` and return 0 (AACLIP_OK) or a negative code; aaclip_last_error() returns the
+ *     message for the calling thread.  There is no CPU fallback: without an sm_100 device calls fail.
+ *   - one context per device; a context is not thread-safe.
+ */
+#ifndef AACLIP_B200_H_
+#define AACLIP_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AACLIP_OK 0
+#define AACLIP_ERR_INVALID (-1)
+#define AACLIP_ERR_CUDA (-2)
+#define AACLIP_ERR_NO_DEVICE (-3)
+#define AACLIP_ERR_STATE (-4)
+
+/* activation of the MLP (model/model.py:84: nn.GELU unless quick_gelu; QuickGELU model/transformer.py:46-49) */
+#define AACLIP_ACT_NONE 0
+#define AACLIP_ACT_GELU_ERF 1
+#define AACLIP_ACT_QUICK_GELU 2
+#define AACLIP_ACT_LEAKY 3 /* nn.LeakyReLU(0.01), model/adapter_modules.py:9,20 */
+
+/* GEMM output modes */
+#define AACLIP_OUT_BF16 0
+#define AACLIP_OUT_F32 1
+#define AACLIP_OUT_F32_RESID 2 /* out += result (fp32 residual stream, model/transformer.py:256-257) */
+#define AACLIP_OUT_F32_PATCH 3 /* patch-embed scatter + positional embedding (model/adapter.py:68-82) */
+
+/* anomaly-map head modes (forward_utils.py:196-216; DOMAINS in dataset/constants.py) */
+#define AACLIP_HEAD_TEST_INDUSTRIAL 0 /* (s1+1-s0)/2, gaussian 7x7 sigma 1, bilinear align_corners */
+#define AACLIP_HEAD_TEST_MEDICAL 1    /* same with gaussian 9x9 sigma 1.5 */
+#define AACLIP_HEAD_TRAIN_SOFTMAX 2   /* bilinear on both channels, softmax over channels, no blur */
+
+/* tensors accepted by aaclip_set_weight; names are the reference state_dict keys */
+typedef enum {
+  /* visual tower: clipmodel.visual.* (model/transformer.py:359-404) */
+  AACLIP_W_V_CONV1 = 0,       /* conv1.weight [width,3,ps,ps] */
+  AACLIP_W_V_CLS = 1,         /* class_embedding [width] */
+  AACLIP_W_V_POS = 2,         /* positional_embedding [L,width] */
+  AACLIP_W_V_LN_PRE_G = 3, AACLIP_W_V_LN_PRE_B = 4,
+  AACLIP_W_V_LN_POST_G = 5, AACLIP_W_V_LN_POST_B = 6,
+  /* per layer: transformer.resblocks.{i}.* (model/transformer.py:183-224) */
+  AACLIP_W_V_LN1_G = 10, AACLIP_W_V_LN1_B = 11,
+  AACLIP_W_V_QKV_W = 12, AACLIP_W_V_QKV_B = 13,    /* attn.in_proj_weight [3w,w], in_proj_bias */
+  AACLIP_W_V_OUT_W = 14, AACLIP_W_V_OUT_B = 15,    /* attn.out_proj.weight [w,w], bias */
+  AACLIP_W_V_LN2_G = 16, AACLIP_W_V_LN2_B = 17,
+  AACLIP_W_V_FC_W = 18, AACLIP_W_V_FC_B = 19,      /* mlp.c_fc [4w,w] */
+  AACLIP_W_V_PROJ_W = 20, AACLIP_W_V_PROJ_B = 21,  /* mlp.c_proj [w,4w] */
+  /* image_adapter.* (model/adapter.py:27-39) */
+  AACLIP_W_I_ADAPTER = 30,    /* layer_adapters.{i}.fc.0.weight [w,w] */
+  AACLIP_W_I_SEG_PROJ = 31,   /* seg_proj.{i}.fc(.0).weight [E,w] */
+  AACLIP_W_I_DET_PROJ = 32,   /* det_proj.fc(.0).weight [E,w] */
+  /* text tower: clipmodel.* (model/model.py:165-174) */
+  AACLIP_W_T_TOKEN_EMB = 40,  /* token_embedding.weight [vocab,tw] */
+  AACLIP_W_T_POS = 41,        /* positional_embedding [ctx,tw] */
+  AACLIP_W_T_LN_FINAL_G = 42, AACLIP_W_T_LN_FINAL_B = 43,
+  AACLIP_W_T_LN1_G = 50, AACLIP_W_T_LN1_B = 51,
+  AACLIP_W_T_QKV_W = 52, AACLIP_W_T_QKV_B = 53,
+  AACLIP_W_T_OUT_W = 54, AACLIP_W_T_OUT_B = 55,
+  AACLIP_W_T_LN2_G = 56, AACLIP_W_T_LN2_B = 57,
+  AACLIP_W_T_FC_W = 58, AACLIP_W_T_FC_B = 59,
+  AACLIP_W_T_PROJ_W = 60, AACLIP_W_T_PROJ_B = 61,
+  /* text_adapter.* (model/adapter.py:41-44) */
+  AACLIP_W_T_ADAPTER = 70,    /* {i}.fc.0.weight [tw,tw], i < text_adapt_until */
+  AACLIP_W_T_FINAL_PROJ = 71  /* {text_adapt_until}.fc.0.weight [tw,tw] (Linear + LeakyReLU) */
+} aaclip_weight_id;
+
+typedef struct {
+  /* visual tower (model/model_configs/ViT-L-14-336.json) */
+  int image_size;   /* 336 (518 for the paper setting, test.py:111) */
+  int patch_size;   /* 14 */
+  int width;        /* 1024 */
+  int heads;        /* 16 (head dim must be 64) */
+  int layers;       /* 24 */
+  int mlp_width;    /* 4096 */
+  int embed_dim;    /* 768 */
+  int act;          /* AACLIP_ACT_GELU_ERF or AACLIP_ACT_QUICK_GELU */
+  /* AdaptedCLIP ctor arguments (model/adapter.py:7-17) */
+  int image_adapt_until;    /* 6 */
+  float image_adapt_weight; /* 0.1 */
+  int n_levels;             /* 4 */
+  int levels[8];            /* {6,12,18,24}: tap after block levels[i] (1-based) */
+  int proj_relu;            /* SimpleProj relu flag (test.py --relu, default 0) */
+  /* text tower; t_layers == 0 disables it */
+  int t_context;    /* 77 */
+  int t_vocab;      /* 49408 */
+  int t_width;      /* 768 */
+  int t_heads;      /* 12 */
+  int t_layers;     /* 12 */
+  int text_adapt_until;     /* 3 */
+  float text_adapt_weight;  /* 0.1 */
+  /* capacity */
+  int max_batch;    /* images per visual forward the workspaces are sized for */
+  int max_text;     /* sentences per text forward */
+  int cta_group;    /* 1 or 2: tcgen05 cta_group used by the GEMMs (0 = library default) */
+} aaclip_cfg;
+
+typedef struct aaclip_ctx aaclip_ctx;
+
+const char* aaclip_last_error(void);
+int aaclip_abi_version(void);
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device);
+void aaclip_destroy(aaclip_ctx* ctx);
+/* Copies `numel` fp32 values from DEVICE or HOST memory (src_is_host) into the context's packed layout
+ * (bf16 for GEMM operands, fp32 otherwise).  `layer` indexes per-layer / per-level tensors, else 0.
+ * Replaces nn.Module.load_state_dict for clipmodel.visual.*, image_adapter.*, text_adapter.* (test.py:163-176). */
+int aaclip_set_weight(aaclip_ctx* ctx, int weight_id, int layer, const float* src, long long numel, int src_is_host,
+                      void* stream);
+/* Bytes of device memory the context holds (weights + workspaces). */
+long long aaclip_device_bytes(const aaclip_ctx* ctx);
+/* Number of kernels the library launched on behalf of ctx since creation (for bench.py gpu_launches). */
+long long aaclip_launch_count(const aaclip_ctx* ctx);
+
+/* ---- AdaptedCLIP.forward (model/adapter.py:67-112) ------------------------------------------------- */
+/* image fp32 [B,3,S,S] (CLIP-normalised).  seg_out[i]: fp32 [B,P,E] L2-normalised patch tokens of level i
+ * (or NULL to skip materialising them); det_out fp32 [B,E] (or NULL). */
+int aaclip_visual_forward(aaclip_ctx* ctx, const float* image, int B, float* const* seg_out, float* det_out,
+                          void* stream);
+
+/* ---- calculate_similarity_map + test.py:83-93 ------------------------------------------------------- */
+/* seg[i]: [B,P,E] fp32 (seg_is_bf16 = 0) or bf16 normalised patch tokens, n_levels of them; anchors fp32
+ * [E,2] (anchors_batched = 0) or [B,E,2]; det fp32 [B,E] or NULL.
+ * maps_out: test modes -> fp32 [B,S,S] = sum over levels of the per-level map (test.py:93);
+ *           train mode -> fp32 [n_levels,B,2,S,S] softmaxed per level (forward_utils.py:214-215).
+ * scores_out: fp32 [B] = ((det . anchors)[:,1] + 1)/2 (test.py:83-84) or NULL. */
+int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors,
+                        int anchors_batched, const float* det, int B, int P, int E, int img_size, int mode,
+                        float* maps_out, float* scores_out, void* stream);
+
+/* ---- fused image -> anomaly map (AdaptedCLIP.forward + head, no seg-token materialisation) ---------- */
+int aaclip_forward_fused(aaclip_ctx* ctx, const float* image, int B, const float* anchors /*[E,2]*/, int mode,
+                         float* maps_out /*[B,S,S]*/, float* scores_out /*[B]*/, void* stream);
+/* Same with HOST buffers (pinned or pageable): H2D of the images, D2H of maps and scores, synchronous. */
+int aaclip_forward_fused_host(aaclip_ctx* ctx, const float* host_image, int B, const float* host_anchors, int mode,
+                              float* host_maps_out, float* host_scores_out);
+
+/* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
+/* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */
+int aaclip_text_forward(aaclip_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);
+
+/* ---- building blocks (exported so the parity tests can pin each kernel on its own) ------------------ */
+/* out = epilogue(A[M,K] . W[N,K]^T), bf16 operands (pitches lda/ldw elements), fp32 accumulation. */
+int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                     void* out, int ldo, int act, int out_mode, const float* pos, int P, int cta_group, void* stream);
+/* LayerNorm (model/transformer.py:37-43), fp32 in -> bf16 and/or fp32 out. */
+int aaclip_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
+                     void* out_bf16, float* out_f32, void* stream);
+/* softmax(q k^T / 8) v per head, head dim 64 (nn.MultiheadAttention core, model/transformer.py:237);
+ * qkv bf16 [B*L, 3*heads*64], out bf16 [B*L, heads*64]; causal != 0 applies CLIP's text mask (model/model.py:172). */
+int aaclip_attention(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream);
+/* adapter mix x <- w*a*||x||/||a|| + (1-w)*x (model/adapter.py:93-99) */
+int aaclip_adapter_mix(float* x, const float* a, float w, int rows, int width, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AACLIP_B200_H_ */
