@@ -1,0 +1,187 @@
+"""Python handle on an `aaclip_ctx` (include/aaclip_b200.h): creation from a ModelCfg, weight upload from
+reference-keyed state dicts, and the forward entry points.  Pure plumbing: pointers in, pointers out."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_QUICK_GELU, HEAD_TEST_INDUSTRIAL, HEAD_TEST_MEDICAL, W, AaclipCfg, check,
+                   cur_stream, ptr)
+from .synth import ModelCfg
+
+DOMAIN_MODE = {"Industrial": HEAD_TEST_INDUSTRIAL, "Medical": HEAD_TEST_MEDICAL}
+
+
+def _block_keys(prefix: str, tower: str):
+    t = tower  # "V" or "T"
+    return [
+        (prefix + "ln_1.weight", W[f"{t}_LN1_G"]), (prefix + "ln_1.bias", W[f"{t}_LN1_B"]),
+        (prefix + "attn.in_proj_weight", W[f"{t}_QKV_W"]), (prefix + "attn.in_proj_bias", W[f"{t}_QKV_B"]),
+        (prefix + "attn.out_proj.weight", W[f"{t}_OUT_W"]), (prefix + "attn.out_proj.bias", W[f"{t}_OUT_B"]),
+        (prefix + "ln_2.weight", W[f"{t}_LN2_G"]), (prefix + "ln_2.bias", W[f"{t}_LN2_B"]),
+        (prefix + "mlp.c_fc.weight", W[f"{t}_FC_W"]), (prefix + "mlp.c_fc.bias", W[f"{t}_FC_B"]),
+        (prefix + "mlp.c_proj.weight", W[f"{t}_PROJ_W"]), (prefix + "mlp.c_proj.bias", W[f"{t}_PROJ_B"]),
+    ]
+
+
+def weight_map(cfg: ModelCfg, text: bool = True) -> Dict[str, tuple]:
+    """state-dict key -> (weight id, layer) for the three reference state dicts, with the prefixes
+    'clip.', 'image_adapter.' and 'text_adapter.' telling them apart."""
+    m: Dict[str, tuple] = {}
+    m["clip.visual.conv1.weight"] = (W["V_CONV1"], 0)
+    m["clip.visual.class_embedding"] = (W["V_CLS"], 0)
+    m["clip.visual.positional_embedding"] = (W["V_POS"], 0)
+    m["clip.visual.ln_pre.weight"] = (W["V_LN_PRE_G"], 0); m["clip.visual.ln_pre.bias"] = (W["V_LN_PRE_B"], 0)
+    m["clip.visual.ln_post.weight"] = (W["V_LN_POST_G"], 0); m["clip.visual.ln_post.bias"] = (W["V_LN_POST_B"], 0)
+    for i in range(cfg.layers):
+        for k, wid in _block_keys(f"visual.transformer.resblocks.{i}.", "V"):
+            m["clip." + k] = (wid, i)
+    fc = "fc.0.weight" if cfg.relu else "fc.weight"
+    for i in range(cfg.image_adapt_until):
+        m[f"image_adapter.layer_adapters.{i}.fc.0.weight"] = (W["I_ADAPTER"], i)
+    for i in range(len(cfg.levels)):
+        m[f"image_adapter.seg_proj.{i}.{fc}"] = (W["I_SEG_PROJ"], i)
+    m[f"image_adapter.det_proj.{fc}"] = (W["I_DET_PROJ"], 0)
+    if text and cfg.t_layers > 0:
+        m["clip.token_embedding.weight"] = (W["T_TOKEN_EMB"], 0)
+        m["clip.positional_embedding"] = (W["T_POS"], 0)
+        m["clip.ln_final.weight"] = (W["T_LN_FINAL_G"], 0); m["clip.ln_final.bias"] = (W["T_LN_FINAL_B"], 0)
+        for i in range(cfg.t_layers):
+            for k, wid in _block_keys(f"transformer.resblocks.{i}.", "T"):
+                m["clip." + k] = (wid, i)
+        for i in range(cfg.text_adapt_until):
+            m[f"text_adapter.{i}.fc.0.weight"] = (W["T_ADAPTER"], i)
+        m[f"text_adapter.{cfg.text_adapt_until}.fc.0.weight"] = (W["T_FINAL_PROJ"], 0)
+    return m
+
+
+class Engine:
+    """One context on one B200.  Not thread-safe (neither is the reference's nn.Module)."""
+
+    def __init__(self, cfg: ModelCfg, device: int = 0, max_batch: int = 64, max_text: int = 16,
+                 text: bool = True, cta_group: int = 0):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = device
+        self.max_batch = max_batch
+        self.has_text = bool(text and cfg.t_layers > 0)
+        c = AaclipCfg()
+        c.image_size, c.patch_size, c.width, c.heads = cfg.image_size, cfg.patch_size, cfg.width, cfg.heads
+        c.layers, c.mlp_width, c.embed_dim = cfg.layers, cfg.mlp_width, cfg.embed_dim
+        c.act = ACT_QUICK_GELU if cfg.quick_gelu else ACT_GELU_ERF
+        c.image_adapt_until, c.image_adapt_weight = cfg.image_adapt_until, cfg.image_adapt_weight
+        c.n_levels = len(cfg.levels)
+        for i, l in enumerate(cfg.levels):
+            c.levels[i] = int(l)
+        c.proj_relu = int(cfg.relu)
+        if self.has_text:
+            c.t_context, c.t_vocab, c.t_width, c.t_heads, c.t_layers = (cfg.t_context, cfg.t_vocab, cfg.t_width,
+                                                                        cfg.t_heads, cfg.t_layers)
+            c.text_adapt_until, c.text_adapt_weight = cfg.text_adapt_until, cfg.text_adapt_weight
+        c.max_batch, c.max_text, c.cta_group = max_batch, max_text, cta_group
+        self._ctx = C.c_void_p()
+        check(self.lib.aaclip_create(C.byref(self._ctx), C.byref(c), device))
+        self._wmap = weight_map(cfg, self.has_text)
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.aaclip_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def set_weight(self, full_key: str, tensor: torch.Tensor) -> None:
+        wid, layer = self._wmap[full_key]
+        t = tensor.detach()
+        if t.dtype != torch.float32:
+            t = t.float()
+        t = t.contiguous()
+        on_host = not t.is_cuda
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.aaclip_set_weight(self._ctx, wid, layer, t.data_ptr(), t.numel(), int(on_host), stream))
+
+    def load_state_dicts(self, clip_sd: Optional[Dict[str, torch.Tensor]] = None,
+                         image_adapter_sd: Optional[Dict[str, torch.Tensor]] = None,
+                         text_adapter_sd: Optional[Dict[str, torch.Tensor]] = None) -> List[str]:
+        """Upload every tensor the hot path reads; returns the keys that were consumed."""
+        used = []
+        for prefix, sd in (("clip.", clip_sd), ("image_adapter.", image_adapter_sd), ("text_adapter.", text_adapter_sd)):
+            if sd is None:
+                continue
+            for k, v in sd.items():
+                fk = prefix + k
+                if fk in self._wmap:
+                    self.set_weight(fk, v)
+                    used.append(fk)
+        torch.cuda.synchronize(self.device)
+        return used
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.aaclip_device_bytes(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.aaclip_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ forward
+    def _check_image(self, image: torch.Tensor) -> None:
+        S = self.cfg.image_size
+        if image.dim() != 4 or tuple(image.shape[1:]) != (3, S, S):
+            raise ValueError(f"image must be [B,3,{S},{S}], got {tuple(image.shape)}")
+        if not image.is_cuda or image.dtype != torch.float32 or not image.is_contiguous():
+            raise ValueError("image must be a contiguous float32 CUDA tensor")
+
+    def visual_forward(self, image: torch.Tensor, want_seg: bool = True, want_det: bool = True):
+        """AdaptedCLIP.forward: returns (list of fp32 [B,P,E], fp32 [B,E])."""
+        self._check_image(image)
+        B = image.shape[0]
+        cfg = self.cfg
+        seg = [torch.empty(B, cfg.patches, cfg.embed_dim, device=image.device, dtype=torch.float32)
+               for _ in cfg.levels] if want_seg else []
+        det = torch.empty(B, cfg.embed_dim, device=image.device, dtype=torch.float32) if want_det else None
+        arr = (C.c_void_p * len(cfg.levels))(*[t.data_ptr() for t in seg]) if want_seg else None
+        check(self.lib.aaclip_visual_forward(self._ctx, ptr(image), B, arr, ptr(det), cur_stream()))
+        return seg, det
+
+    def forward_fused(self, image: torch.Tensor, anchors: torch.Tensor, domain: str = "Industrial",
+                      want_maps: bool = True, want_scores: bool = True):
+        """image -> (level-summed anomaly maps fp32 [B,S,S], image scores fp32 [B]) without seg tokens."""
+        self._check_image(image)
+        if tuple(anchors.shape) != (self.cfg.embed_dim, 2) or anchors.dtype != torch.float32 or not anchors.is_cuda:
+            raise ValueError("anchors must be a float32 CUDA tensor [E,2]")
+        B, S = image.shape[0], self.cfg.image_size
+        maps = torch.empty(B, S, S, device=image.device, dtype=torch.float32) if want_maps else None
+        scores = torch.empty(B, device=image.device, dtype=torch.float32) if want_scores else None
+        check(self.lib.aaclip_forward_fused(self._ctx, ptr(image), B, ptr(anchors.contiguous()), DOMAIN_MODE[domain],
+                                            ptr(maps), ptr(scores), cur_stream()))
+        return maps, scores
+
+    def forward_fused_host(self, image: torch.Tensor, anchors: torch.Tensor, maps_out: torch.Tensor,
+                           scores_out: torch.Tensor, domain: str = "Industrial") -> None:
+        """Host-buffer entry: `image`, `anchors`, `maps_out`, `scores_out` are CPU tensors (pinned for speed);
+        H2D, compute and D2H all happen inside the call, which returns after the results have landed."""
+        for t in (image, anchors, maps_out, scores_out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("forward_fused_host takes contiguous float32 CPU tensors")
+        check(self.lib.aaclip_forward_fused_host(self._ctx, image.data_ptr(), image.shape[0], anchors.data_ptr(),
+                                                 DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr()))
+
+    def text_forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        """AdaptedCLIP.encode_text(adapt_text=True): int32 [n, ctx] -> fp32 [n, t_width]."""
+        if not self.has_text:
+            raise RuntimeError("engine was created without the text tower")
+        if tokens.dim() != 2 or tokens.shape[1] != self.cfg.t_context:
+            raise ValueError(f"tokens must be [n,{self.cfg.t_context}]")
+        tk = tokens.to(device=f"cuda:{self.device}", dtype=torch.int32).contiguous()
+        out = torch.empty(tk.shape[0], self.cfg.t_width, device=tk.device, dtype=torch.float32)
+        check(self.lib.aaclip_text_forward(self._ctx, ptr(tk), tk.shape[0], ptr(out), cur_stream()))
+        return out

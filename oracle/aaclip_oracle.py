@@ -1,0 +1,197 @@
+"""ORACLE — test infrastructure only.  NOT part of the product path.
+
+A CPU, fp32, plain-PyTorch restatement of the reference (wei-paul/AA-CLIP) inference hot path, written
+against state dicts so that it runs where /root/reference does not exist (the GPU box).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module; the
+package aaclip_b200 never does.
+
+Pinning: the reference ships no tests and no golden vectors, so the restatement is pinned
+against the REAL reference modules imported from /root/reference by oracle/make_golden.py, which also
+writes tests/golden/*.pt; tests/test_oracle_golden.py re-checks the oracle against those files wherever
+it runs.  One boundary stays unpinned: `gaussian_blur2d` lives in the un-vendored third-party dependency
+kornia==0.6.9 (requirements.txt:3, call site forward_utils.py:208-210), absent offline — it is restated
+below from kornia 0.6.9's published algorithm and marked "parity unpinned (kornia)".
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+# ----------------------------------------------------------------------------------------------- blocks
+def layer_norm(x: torch.Tensor, sd: SD, prefix: str, eps: float = 1e-5) -> torch.Tensor:
+    """model/transformer.py:37-43 (LayerNorm.forward -> F.layer_norm, eps default 1e-5)."""
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], eps)
+
+
+def activation(x: torch.Tensor, quick_gelu: bool) -> torch.Tensor:
+    """nn.GELU (exact erf) unless quick_gelu (model/model.py:84); QuickGELU model/transformer.py:46-49."""
+    return x * torch.sigmoid(1.702 * x) if quick_gelu else F.gelu(x)
+
+
+def multi_head_attention(x: torch.Tensor, sd: SD, prefix: str, heads: int,
+                         attn_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """nn.MultiheadAttention(q=k=v=x) as called at model/transformer.py:226-237: packed in-proj, q scaled by
+    1/sqrt(head_dim), additive mask, softmax, out-proj.  x is [B, L, D] (batch-first restatement of the
+    reference's LND layout; the arithmetic per token is identical)."""
+    B, L, D = x.shape
+    hd = D // heads
+    qkv = F.linear(x, sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"])
+    q, k, v = qkv.view(B, L, 3, heads, hd).permute(2, 0, 3, 1, 4)  # each [B, h, L, hd]
+    s = (q * (1.0 / math.sqrt(hd))) @ k.transpose(-1, -2)
+    if attn_mask is not None:
+        s = s + attn_mask
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B, L, D)
+    return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
+
+
+def residual_attention_block(x: torch.Tensor, sd: SD, prefix: str, heads: int, quick_gelu: bool,
+                             attn_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """model/transformer.py:239-258 with ls_1 = ls_2 = Identity (:201-205, :220-224)."""
+    x = x + multi_head_attention(layer_norm(x, sd, prefix + "ln_1."), sd, prefix + "attn.", heads, attn_mask)
+    h = F.linear(layer_norm(x, sd, prefix + "ln_2."), sd[prefix + "mlp.c_fc.weight"], sd[prefix + "mlp.c_fc.bias"])
+    h = activation(h, quick_gelu)
+    return x + F.linear(h, sd[prefix + "mlp.c_proj.weight"], sd[prefix + "mlp.c_proj.bias"])
+
+
+def adapter_mix(x: torch.Tensor, w_adapter: torch.Tensor, weight: float) -> torch.Tensor:
+    """model/adapter.py:92-99: SimpleAdapter = Linear(bias=False) + LeakyReLU (model/adapter_modules.py:6-13),
+    norm matched to x over the last dim (no epsilon), then i_w * a + (1 - i_w) * x."""
+    a = F.leaky_relu(F.linear(x, w_adapter), 0.01)
+    a = a * x.norm(dim=-1, keepdim=True) / a.norm(dim=-1, keepdim=True)
+    return weight * a + (1 - weight) * x
+
+
+def simple_proj(x: torch.Tensor, sd: SD, prefix: str) -> torch.Tensor:
+    """model/adapter_modules.py:16-26: key `fc.0.weight` (Linear + LeakyReLU) iff relu else `fc.weight`."""
+    if prefix + "fc.0.weight" in sd:
+        return F.leaky_relu(F.linear(x, sd[prefix + "fc.0.weight"]), 0.01)
+    return F.linear(x, sd[prefix + "fc.weight"])
+
+
+# ----------------------------------------------------------------------------------------------- visual
+def visual_forward(clip_sd: SD, image_adapter_sd: SD, image: torch.Tensor, *, patch_size: int = 14, heads: int = 16,
+                   layers: int = 24, image_adapt_until: int = 6, image_adapt_weight: float = 0.1,
+                   levels: Sequence[int] = (6, 12, 18, 24), quick_gelu: bool = False,
+                   return_taps: bool = False):
+    """AdaptedCLIP.forward, model/adapter.py:67-112.  Returns (seg_tokens: list of [B,P,E], det_token [B,E])."""
+    sd = clip_sd
+    x = F.conv2d(image, sd["visual.conv1.weight"], stride=patch_size)          # :68
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)                 # :69-70
+    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype)
+    x = torch.cat([cls, x], dim=1)                                             # :72-81
+    x = x + sd["visual.positional_embedding"]                                  # :82
+    x = layer_norm(x, sd, "visual.ln_pre.")                                    # :84-85 (patch_dropout = identity)
+    tokens = []
+    for i in range(layers):                                                    # :90
+        x = residual_attention_block(x, sd, f"visual.transformer.resblocks.{i}.", heads, quick_gelu, None)
+        if i < image_adapt_until:                                              # :92-99
+            x = adapter_mix(x, image_adapter_sd[f"layer_adapters.{i}.fc.0.weight"], image_adapt_weight)
+        if i + 1 in levels:                                                    # :100-101
+            tokens.append(x[:, 1:, :])
+    taps = tokens
+    tokens = [layer_norm(t, sd, "visual.ln_post.") for t in tokens]            # :105
+    seg = [simple_proj(t, image_adapter_sd, f"seg_proj.{i}.") for i, t in enumerate(tokens)]   # :106-108
+    seg = [F.normalize(t, dim=-1) for t in seg]                                # :109
+    det = simple_proj(tokens[-1], image_adapter_sd, "det_proj.")               # :110
+    det = F.normalize(det, dim=-1).mean(1)                                     # :111
+    if return_taps:
+        return seg, det, taps
+    return seg, det
+
+
+# ----------------------------------------------------------------------------------------------- text
+def causal_mask(n: int) -> torch.Tensor:
+    """CLIP.attn_mask (model/model.py:172; build_attention_mask transformer.py:629-635)."""
+    return torch.full((n, n), float("-inf")).triu_(1)
+
+
+def encode_text(clip_sd: SD, text_adapter_sd: SD, tokens: torch.Tensor, *, heads: int = 12, layers: int = 12,
+                text_adapt_until: int = 3, text_adapt_weight: float = 0.1, quick_gelu: bool = False) -> torch.Tensor:
+    """AdaptedCLIP.encode_text(adapt_text=True), model/adapter.py:114-145.  tokens int [n, ctx] -> [n, width]."""
+    sd = clip_sd
+    x = F.embedding(tokens.long(), sd["token_embedding.weight"])               # :118
+    x = x + sd["positional_embedding"]                                         # :122
+    mask = causal_mask(tokens.shape[1])
+    for i in range(layers):                                                    # :125-136
+        x = residual_attention_block(x, sd, f"transformer.resblocks.{i}.", heads, quick_gelu, mask)
+        if i < text_adapt_until:
+            x = adapter_mix(x, text_adapter_sd[f"{i}.fc.0.weight"], text_adapt_weight)
+    x = layer_norm(x, sd, "ln_final.")                                         # :138
+    eot = x[torch.arange(x.shape[0]), tokens.argmax(dim=-1)]                   # :140
+    return F.leaky_relu(F.linear(eot, text_adapter_sd[f"{text_adapt_until}.fc.0.weight"]), 0.01)
+
+
+def class_text_anchor(emb_normal: torch.Tensor, emb_abnormal: torch.Tensor) -> torch.Tensor:
+    """forward_utils.py:155-161: per-sentence L2 norm -> mean -> L2 norm, stacked to [width, 2]."""
+    cols = []
+    for e in (emb_normal, emb_abnormal):
+        e = e / e.norm(dim=-1, keepdim=True)
+        m = e.mean(dim=0)
+        cols.append(m / m.norm())
+    return torch.stack(cols, dim=1)
+
+
+# ----------------------------------------------------------------------------------------------- head
+def gaussian_kernel1d(ksize: int, sigma: float) -> torch.Tensor:
+    """kornia 0.6.9 kornia/filters/kernels.py::gaussian: x = arange(k) - k//2 (+0.5 if k even),
+    exp(-x^2 / (2 sigma^2)), normalised to sum 1.   [parity unpinned (kornia)]"""
+    x = torch.arange(ksize, dtype=torch.float32) - ksize // 2
+    if ksize % 2 == 0:
+        x = x + 0.5
+    g = torch.exp(-x.pow(2.0) / (2 * sigma ** 2))
+    return g / g.sum()
+
+
+def gaussian_blur2d(x: torch.Tensor, kernel_size: Tuple[int, int], sigma: Tuple[float, float]) -> torch.Tensor:
+    """kornia 0.6.9 gaussian_blur2d(input, kernel_size, sigma, border_type='reflect', separable=True):
+    reflect-pad by k//2 and correlate every channel with the (separable) normalised Gaussian.
+    [parity unpinned (kornia): un-vendored dependency, restated from its published algorithm]"""
+    ky, kx = kernel_size
+    gy, gx = gaussian_kernel1d(ky, sigma[1]), gaussian_kernel1d(kx, sigma[0])
+    b, c, h, w = x.shape
+    xp = F.pad(x, (kx // 2, kx // 2, ky // 2, ky // 2), mode="reflect")
+    k2d = torch.outer(gy, gx).to(x.dtype)[None, None].expand(c, 1, ky, kx)
+    return F.conv2d(xp, k2d, groups=c)
+
+
+def calculate_similarity_map(patch_features: torch.Tensor, text_feature: torch.Tensor, img_size: int,
+                             test: bool = False, domain: str = "Medical") -> torch.Tensor:
+    """forward_utils.py:196-216, line for line."""
+    scores = 100.0 * torch.matmul(patch_features, text_feature)                # :199
+    B, L, C = scores.shape
+    H = int(math.sqrt(L))                                                      # :201
+    pred = scores.permute(0, 2, 1).reshape(B, C, H, H)                         # :202
+    if test:
+        assert C == 2                                                          # :204
+        sigma = 1 if domain == "Industrial" else 1.5
+        ksize = 7 if domain == "Industrial" else 9
+        pred = (pred[:, 1] + 1 - pred[:, 0]) / 2                               # :207
+        pred = gaussian_blur2d(pred.unsqueeze(1), (ksize, ksize), (sigma, sigma))   # :208-210
+    out = F.interpolate(pred, size=img_size, mode="bilinear", align_corners=True)   # :211-213
+    if not test and C > 1:
+        out = torch.softmax(out, dim=1)                                        # :214-215
+    return out
+
+
+def predict(seg_tokens: List[torch.Tensor], det_token: torch.Tensor, text_feature: torch.Tensor, img_size: int,
+            domain: str = "Industrial") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Body of test.py:get_predictions for one batch (test.py:83-93): image score and level-summed map."""
+    pred = det_token @ text_feature
+    score = (pred[:, 1] + 1) / 2                                               # test.py:83-84
+    maps = [calculate_similarity_map(f, text_feature, img_size, test=True, domain=domain) for f in seg_tokens]
+    return torch.cat(maps, dim=1).sum(1), score                                # test.py:93
+
+
+def minmax_normalise(maps: torch.Tensor) -> torch.Tensor:
+    """forward_utils.py:241-244 (metrics_eval): (x - min) / (max - min) over the whole set."""
+    lo, hi = maps.min(), maps.max()
+    return (maps - lo) / (hi - lo)
