@@ -27,6 +27,11 @@ W = dict(
 )
 
 
+PROFILE_CLASSES = ["gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj", "gemm_adapter", "gemm_segdet", "gemm_patch",
+                   "attention", "layernorm", "adapter_mix", "cast", "l2norm", "det_mean", "stem_misc", "head_maps",
+                   "other"]
+
+
 class AaclipCfg(C.Structure):
     _fields_ = [
         ("image_size", C.c_int), ("patch_size", C.c_int), ("width", C.c_int), ("heads", C.c_int),
@@ -49,11 +54,14 @@ SIGNATURES = {
     "aaclip_set_weight": (_i, [_vp, _i, _i, _vp, _ll, _i, _vp]),
     "aaclip_device_bytes": (_ll, [_vp]),
     "aaclip_launch_count": (_ll, [_vp]),
+    "aaclip_profile_enable": (_i, [_vp, _i]),
+    "aaclip_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll), _i]),
     "aaclip_visual_forward": (_i, [_vp, _vp, _i, C.POINTER(_vp), _vp, _vp]),
     "aaclip_anomaly_head": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "aaclip_forward_fused": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "aaclip_forward_fused_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "aaclip_text_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "aaclip_text_anchor": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "aaclip_gemm_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "aaclip_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "aaclip_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

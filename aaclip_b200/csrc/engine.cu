@@ -91,7 +91,17 @@ struct Tower {
 
 }  // namespace
 
+// kernel classes for the optional per-launch CUDA-event profile (aaclip_profile_*)
+enum ProfClass : int {
+  PC_GEMM_QKV = 0, PC_GEMM_OUT, PC_GEMM_FC, PC_GEMM_PROJ, PC_GEMM_ADAPTER, PC_GEMM_SEGDET, PC_GEMM_PATCH,
+  PC_ATTENTION, PC_LAYERNORM, PC_ADAPTER_MIX, PC_CAST, PC_L2NORM, PC_DET_MEAN, PC_STEM_MISC, PC_HEAD_MAPS,
+  PC_OTHER, PC_COUNT
+};
+struct ProfRec { int cls; cudaEvent_t a, b; };
+
 struct aaclip_ctx {
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
   aaclip_cfg cfg;
   int device = 0;
   int G = 0, P = 0, L = 0, Kpad = 0, E = 0;
@@ -138,6 +148,26 @@ namespace {
     if (_rc) return _rc;     \
   } while (0)
 
+inline void prof_begin(aaclip_ctx* c, int cls, cudaStream_t st) {
+  if (!c->prof_on) return;
+  ProfRec r; r.cls = cls;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  c->prof.push_back(r);
+}
+inline void prof_end(aaclip_ctx* c, cudaStream_t st) {
+  if (c->prof_on) cudaEventRecord(c->prof.back().b, st);
+}
+// launch one kernel of class CLS: count it, and bracket it with events when profiling is on
+#define RUN(CLS, expr)             \
+  do {                             \
+    prof_begin(c, CLS, st);        \
+    int _rc = (expr);              \
+    if (_rc) return _rc;           \
+    prof_end(c, st);               \
+    c->launches++;                 \
+  } while (0)
+
 int alloc_tower(aaclip_ctx* c, Tower& t, int n_adapters) {
   const long long w = t.width, ff = t.mlp;
   t.lw.resize(t.layers);
@@ -162,28 +192,27 @@ int run_block(aaclip_ctx* c, const Tower& t, int i, int B, int L, int causal, fl
   const int cg = c->cta_group;
   const float eps = 1e-5f;
   if (!*xn_ready) {
-    TRY(k::launch_layernorm(c->x, l.ln1_g, l.ln1_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st)); c->launches++;
+    RUN(PC_LAYERNORM, k::launch_layernorm(c->x, l.ln1_g, l.ln1_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st));
   }
   *xn_ready = false;
-  TRY(k::launch_gemm(c->xn, w, l.qkv_w, w, rows, 3 * w, w, l.qkv_b, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
-                     nullptr, 0, cg, st)); c->launches++;
-  TRY(k::launch_attention(c->qkv, c->att, B, L, t.heads, causal, st)); c->launches++;
-  TRY(k::launch_gemm(c->att, w, l.out_w, w, rows, w, w, l.out_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
-                     nullptr, 0, cg, st)); c->launches++;
-  TRY(k::launch_layernorm(c->x, l.ln2_g, l.ln2_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st)); c->launches++;
-  TRY(k::launch_gemm(c->xn, w, l.fc_w, w, rows, ff, w, l.fc_b, c->h, ff, c->cfg.act, gemm::OUT_BF16, nullptr, 0, cg,
-                     st)); c->launches++;
-  TRY(k::launch_gemm(c->h, ff, l.proj_w, ff, rows, w, ff, l.proj_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
-                     nullptr, 0, cg, st)); c->launches++;
+  RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_w, w, rows, 3 * w, w, l.qkv_b, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
+                     nullptr, 0, cg, st));
+  RUN(PC_ATTENTION, k::launch_attention(c->qkv, c->att, B, L, t.heads, causal, st));
+  RUN(PC_GEMM_OUT, k::launch_gemm(c->att, w, l.out_w, w, rows, w, w, l.out_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
+                     nullptr, 0, cg, st));
+  RUN(PC_LAYERNORM, k::launch_layernorm(c->x, l.ln2_g, l.ln2_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st));
+  RUN(PC_GEMM_FC, k::launch_gemm(c->xn, w, l.fc_w, w, rows, ff, w, l.fc_b, c->h, ff, c->cfg.act, gemm::OUT_BF16, nullptr, 0, cg,
+                     st));
+  RUN(PC_GEMM_PROJ, k::launch_gemm(c->h, ff, l.proj_w, ff, rows, w, ff, l.proj_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
+                     nullptr, 0, cg, st));
   if (i < (int)t.adapters.size()) {
     // adapter branch (model/adapter.py:92-99): a = LeakyReLU(x W_a^T); x <- w a |x|/|a| + (1-w) x
-    TRY(k::launch_cast_bf16(c->x, c->xn, (long long)rows * w, st)); c->launches++;
-    TRY(k::launch_gemm(c->xn, w, t.adapters[i], w, rows, w, w, nullptr, c->a, w, gemm::ACT_LEAKY, gemm::OUT_F32,
-                       nullptr, 0, cg, st)); c->launches++;
+    RUN(PC_CAST, k::launch_cast_bf16(c->x, c->xn, (long long)rows * w, st));
+    RUN(PC_GEMM_ADAPTER, k::launch_gemm(c->xn, w, t.adapters[i], w, rows, w, w, nullptr, c->a, w, gemm::ACT_LEAKY, gemm::OUT_F32,
+                       nullptr, 0, cg, st));
     const bool fuse_ln = (i + 1 < t.layers);
-    TRY(k::launch_adapter_mix(c->x, c->a, adapt_w, rows, w, fuse_ln ? t.lw[i + 1].ln1_g : nullptr,
+    RUN(PC_ADAPTER_MIX, k::launch_adapter_mix(c->x, c->a, adapt_w, rows, w, fuse_ln ? t.lw[i + 1].ln1_g : nullptr,
                               fuse_ln ? t.lw[i + 1].ln1_b : nullptr, eps, fuse_ln ? c->xn : nullptr, st));
-    c->launches++;
     *xn_ready = fuse_ln;
   }
   return host::OK;
@@ -197,11 +226,11 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
   const int w = cfg.width, L = c->L, P = c->P, E = c->E, rows = B * L, prow = B * P;
   const int cg = c->cta_group;
   // stem: conv1 as im2col GEMM, +pos, class token, ln_pre (model/adapter.py:68-85)
-  TRY(k::launch_im2col(image, B, cfg.image_size, cfg.patch_size, c->Kpad, c->col, st)); c->launches++;
-  TRY(k::launch_gemm(c->col, c->Kpad, c->conv_w, c->Kpad, prow, w, c->Kpad, nullptr, c->x, w, gemm::ACT_NONE,
-                     gemm::OUT_F32_PATCH, c->pos, P, cg, st)); c->launches++;
-  TRY(k::launch_cls_rows(c->x, c->cls, c->pos, B, L, w, st)); c->launches++;
-  TRY(k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, nullptr, c->x, st)); c->launches++;
+  RUN(PC_STEM_MISC, k::launch_im2col(image, B, cfg.image_size, cfg.patch_size, c->Kpad, c->col, st));
+  RUN(PC_GEMM_PATCH, k::launch_gemm(c->col, c->Kpad, c->conv_w, c->Kpad, prow, w, c->Kpad, nullptr, c->x, w, gemm::ACT_NONE,
+                     gemm::OUT_F32_PATCH, c->pos, P, cg, st));
+  RUN(PC_STEM_MISC, k::launch_cls_rows(c->x, c->cls, c->pos, B, L, w, st));
+  RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, nullptr, c->x, st));
   bool xn_ready = false;
   int level = 0;
   for (int i = 0; i < cfg.layers; ++i) {
@@ -209,20 +238,18 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
     if (level < cfg.n_levels && cfg.levels[level] == i + 1) {
       const bool last = (level == cfg.n_levels - 1);
       // tap: x[:, 1:, :] -> ln_post -> seg_proj (and det_proj on the last tap)   (model/adapter.py:100-111)
-      TRY(k::launch_layernorm(c->x, c->ln_post_g, c->ln_post_b, 1e-5f, prow, w, P, 1, (long long)L * w, c->tap,
-                              nullptr, st)); c->launches++;
+      RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_post_g, c->ln_post_b, 1e-5f, prow, w, P, 1, (long long)L * w, c->tap,
+                              nullptr, st));
       const bool want_det = last && (det_out != nullptr);
       const int n_out = want_det ? 2 * E : E;
-      TRY(k::launch_gemm(c->tap, w, c->segdet_w[level], w, prow, n_out, w, nullptr, c->s, 2 * E,
+      RUN(PC_GEMM_SEGDET, k::launch_gemm(c->tap, w, c->segdet_w[level], w, prow, n_out, w, nullptr, c->s, 2 * E,
                          cfg.proj_relu ? gemm::ACT_LEAKY : gemm::ACT_NONE, gemm::OUT_F32, nullptr, 0, cg, st));
-      c->launches++;
       float* so = (seg_out && seg_out[level]) ? seg_out[level] + seg_off : nullptr;
       float* dl = dots ? dots + (size_t)level * prow * 2 : nullptr;
       if (so || dl) {
-        TRY(k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
-        c->launches++;
+        RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
       }
-      if (want_det) { TRY(k::launch_det_mean(c->s, 2 * E, E, B, P, E, det_out, st)); c->launches++; }
+      if (want_det) RUN(PC_DET_MEAN, k::launch_det_mean(c->s, 2 * E, E, B, P, E, det_out, st));
       ++level;
     }
   }
@@ -321,6 +348,28 @@ extern "C" void aaclip_destroy(aaclip_ctx* c) {
   if (c->stage) cudaFree(c->stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
+}
+
+extern "C" int aaclip_profile_enable(aaclip_ctx* c, int on) {
+  if (!c) return host::fail(host::ERR_INVALID, "null context");
+  c->prof_on = (on != 0);
+  return host::OK;
+}
+
+// Sums the CUDA-event durations recorded since the last read into ms[cls] / counts[cls] (n_classes entries,
+// class order = ProfClass) and clears the records.  Synchronises the device.
+extern "C" int aaclip_profile_read(aaclip_ctx* c, double* ms, long long* counts, int n_classes) {
+  if (!c || !ms || !counts) return host::fail(host::ERR_INVALID, "profile_read: null argument");
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  AACLIP_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  for (auto& r : c->prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls < n_classes) { ms[r.cls] += t; counts[r.cls]++; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  c->prof.clear();
+  return host::OK;
 }
 
 extern "C" long long aaclip_device_bytes(const aaclip_ctx* c) { return c ? c->bytes : 0; }
@@ -445,10 +494,9 @@ extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, co
     const int nb = std::min(c->cfg.max_batch, B - b0);
     TRY(visual_chunk(c, image + b0 * img_elems, nb, nullptr, 0, c->det, anchors, c->dots, st));
     if (maps_out) {
-      TRY(k::launch_head_maps(c->dots, nb, c->G, S, mode, c->cfg.n_levels, maps_out + (long long)b0 * S * S, st));
-      c->launches++;
+      RUN(PC_HEAD_MAPS, k::launch_head_maps(c->dots, nb, c->G, S, mode, c->cfg.n_levels, maps_out + (long long)b0 * S * S, st));
     }
-    if (scores_out) { TRY(k::launch_scores(c->det, anchors, 0, nb, c->E, scores_out + b0, st)); c->launches++; }
+    if (scores_out) { RUN(PC_OTHER, k::launch_scores(c->det, anchors, 0, nb, c->E, scores_out + b0, st)); }
   }
   return host::OK;
 }
@@ -504,10 +552,9 @@ extern "C" int aaclip_text_forward(aaclip_ctx* c, const int32_t* tokens, int n, 
     // ln_final is row-wise, so gather the EOT rows first, then normalise only those (model/adapter.py:138-140)
     eot_gather_kernel<<<nn, 256, 0, st>>>(tk, c->x, ctx, tw, c->a);
     AACLIP_CUDA_CHECK(cudaGetLastError()); c->launches++;
-    TRY(k::launch_layernorm(c->a, c->ln_final_g, c->ln_final_b, 1e-5f, nn, tw, 0, 0, 0, c->xn, nullptr, st));
-    c->launches++;
-    TRY(k::launch_gemm(c->xn, tw, c->t_final, tw, nn, tw, tw, nullptr, out + (long long)n0 * tw, tw, gemm::ACT_LEAKY,
-                       gemm::OUT_F32, nullptr, 0, c->cta_group, st)); c->launches++;
+    RUN(PC_LAYERNORM, k::launch_layernorm(c->a, c->ln_final_g, c->ln_final_b, 1e-5f, nn, tw, 0, 0, 0, c->xn, nullptr, st));
+    RUN(PC_OTHER, k::launch_gemm(c->xn, tw, c->t_final, tw, nn, tw, tw, nullptr, out + (long long)n0 * tw, tw, gemm::ACT_LEAKY,
+                       gemm::OUT_F32, nullptr, 0, c->cta_group, st));
   }
   return host::OK;
 }

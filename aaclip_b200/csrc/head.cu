@@ -190,6 +190,39 @@ __global__ void scores_kernel(const float* __restrict__ det, const float* __rest
   if (lane == 0) scores[b] = (acc + 1.0f) * 0.5f;
 }
 
+
+// forward_utils.py:155-161: rows L2-normalised, averaged, average L2-normalised; written to column `col`
+// of anchors [width, 2].  One block; n is a handful of prompt sentences.
+__global__ void __launch_bounds__(256)
+text_anchor_kernel(const float* __restrict__ emb, int n, int width, float* __restrict__ anchors, int col) {
+  extern __shared__ float sh[];  // [n] inverse row norms, then [8] partial sums
+  float* inv = sh;
+  float* part = sh + n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < n; r += 8) {
+    float ss = 0.f;
+    for (int c = lane; c < width; c += 32) { const float v = emb[(size_t)r * width + c]; ss += v * v; }
+    ss = ptx::warp_sum(ss);
+    if (lane == 0) inv[r] = 1.0f / sqrtf(ss);
+  }
+  __syncthreads();
+  float local = 0.f;
+  for (int c = threadIdx.x; c < width; c += 256) {
+    float acc = 0.f;
+    for (int r = 0; r < n; ++r) acc += emb[(size_t)r * width + c] * inv[r];
+    acc /= float(n);
+    anchors[c * 2 + col] = acc;  // un-normalised mean, fixed up below
+    local += acc * acc;
+  }
+  local = ptx::warp_sum(local);
+  if (lane == 0) part[warp] = local;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < 8; ++i) tot += part[i];
+  const float invn = 1.0f / sqrtf(tot);
+  for (int c = threadIdx.x; c < width; c += 256) anchors[c * 2 + col] *= invn;
+}
+
 }  // namespace
 
 int k::launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors,
@@ -269,5 +302,13 @@ extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg
     int rc = k::launch_scores(det, anchors, anchors_batched, B, E, scores_out, stream);
     if (rc) return rc;
   }
+  return host::OK;
+}
+
+extern "C" int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int col, void* stream_) {
+  if (!emb || !anchors || n <= 0 || width <= 0 || (col != 0 && col != 1))
+    return host::fail(host::ERR_INVALID, "text_anchor: bad argument");
+  text_anchor_kernel<<<1, 256, (n + 8) * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(emb, n, width, anchors, col);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }

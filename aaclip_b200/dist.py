@@ -1,0 +1,49 @@
+"""Data-parallel sharding of an image batch over the GPUs of one box.
+
+Every image is an independent unit (per-sample LayerNorm / attention, shared anchors), so ranks take
+contiguous shards of the batch, keep their anomaly maps local and exchange nothing on the data path; the
+only collective is one all-gather of the per-image scores (B/R floats per rank) over NCCL / NVLink, which
+the reference has no counterpart for (it is single-device: test.py:140-141).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of `total` items owned by `rank`; the first total % world ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_scores(local: torch.Tensor, total: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather per-image scores of unevenly sharded batches into one [total] tensor on every rank.
+
+    `local` holds this rank's shard_range(total, rank, world) scores.  Shards are padded to the largest shard
+    so a single fixed-size all_gather (NCCL on GPUs, gloo in the CPU tests) suffices.
+    """
+    if not dist.is_available() or not dist.is_initialized():
+        if local.numel() != total:
+            raise ValueError("single-process gather needs the full batch")
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    b, e = shard_range(total, rank, world)
+    if local.numel() != e - b:
+        raise ValueError(f"rank {rank} holds {local.numel()} scores, expected {e - b}")
+    width = -(-total // world)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: e - b] = local
+    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = []
+    for r in range(world):
+        rb, re_ = shard_range(total, r, world)
+        parts.append(out[r * width: r * width + (re_ - rb)])
+    return torch.cat(parts)

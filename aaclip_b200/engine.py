@@ -132,6 +132,17 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.aaclip_launch_count(self._ctx))
 
+    def profile(self, on: bool) -> None:
+        check(self.lib.aaclip_profile_enable(self._ctx, int(on)))
+
+    def profile_read(self) -> Dict[str, tuple]:
+        """{kernel class: (total ms, launches)} since the last read (CUDA events around every launch)."""
+        n = len(_lib.PROFILE_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        check(self.lib.aaclip_profile_read(self._ctx, ms, cnt, n))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROFILE_CLASSES)}
+
     # ------------------------------------------------------------------ forward
     def _check_image(self, image: torch.Tensor) -> None:
         S = self.cfg.image_size

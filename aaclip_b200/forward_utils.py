@@ -1,0 +1,68 @@
+"""Drop-ins for the hot-path functions of the reference's forward_utils.py, backed by the CUDA head kernels.
+
+  calculate_similarity_map     forward_utils.py:196-216   (same signature, same return shapes)
+  class_text_embedding         forward_utils.py:153-161   (tokenised prompts -> [768, 2] anchor)
+  get_predictions_batch        test.py:80-93               (fused: image batch -> summed maps + image scores)
+
+String work (prompt tables, BPE tokenizer: dataset/constants.py, model/tokenizer.py) stays with the caller:
+`class_text_embedding` starts from token ids.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import ops
+
+DOMAIN_MODE = {"Industrial": ops.HEAD_TEST_INDUSTRIAL, "Medical": ops.HEAD_TEST_MEDICAL}
+
+
+def _mode(test: bool, domain: str) -> int:
+    if not test:
+        return ops.HEAD_TRAIN_SOFTMAX
+    # forward_utils.py:205-206: anything that is not "Industrial" takes the 9x9 / sigma 1.5 branch
+    return ops.HEAD_TEST_INDUSTRIAL if domain == "Industrial" else ops.HEAD_TEST_MEDICAL
+
+
+@torch.no_grad()
+def calculate_similarity_map(patch_features: torch.Tensor, epoch_text_feature: torch.Tensor, img_size: int,
+                             test: bool = False, domain: str = "Medical") -> torch.Tensor:
+    """[B,L,768] x ([768,C] | [B,768,C]) -> test: [B,1,img,img]; train: [B,C,img,img] softmaxed (C == 2)."""
+    if epoch_text_feature.shape[-1] != 2:
+        # the reference asserts C == 2 in test mode (forward_utils.py:204); the kernels are built for C == 2
+        raise AssertionError("calculate_similarity_map: C must be 2")
+    pf = patch_features if patch_features.dtype in (torch.float32, torch.bfloat16) else patch_features.float()
+    maps, _ = ops.anomaly_head([pf.contiguous()], epoch_text_feature.float().contiguous(), int(img_size),
+                               _mode(test, domain))
+    if test:
+        return maps.unsqueeze(1)
+    return maps[0]
+
+
+@torch.no_grad()
+def similarity_maps_summed(patch_features: Sequence[torch.Tensor], epoch_text_feature: torch.Tensor, img_size: int,
+                           domain: str = "Industrial", det_feature: torch.Tensor = None):
+    """test.py:83-93 in one call: torch.cat([calculate_similarity_map(f, ..., test=True) ...], 1).sum(1) and
+    (optionally) the image score ((det @ T)[:, 1] + 1) / 2."""
+    feats = [f.contiguous() for f in patch_features]
+    return ops.anomaly_head(feats, epoch_text_feature.float().contiguous(), int(img_size), _mode(True, domain),
+                            det=None if det_feature is None else det_feature.float().contiguous())
+
+
+@torch.no_grad()
+def class_text_embedding(model, tokens_normal: torch.Tensor, tokens_abnormal: torch.Tensor) -> torch.Tensor:
+    """forward_utils.py:147-161 from token ids: encode_text -> row L2 norm -> mean -> L2 norm, stacked [768,2]."""
+    from ._lib import check, cur_stream, load, ptr
+    embs = [model.encode_text(t) for t in (tokens_normal, tokens_abnormal)]
+    out = torch.empty(embs[0].shape[1], 2, device=embs[0].device, dtype=torch.float32)
+    lib = load()
+    for col, e in enumerate(embs):
+        check(lib.aaclip_text_anchor(ptr(e), e.shape[0], e.shape[1], ptr(out), col, cur_stream()))
+    return out
+
+
+@torch.no_grad()
+def get_predictions_batch(model, image: torch.Tensor, epoch_text_feature: torch.Tensor, domain: str = "Industrial"):
+    """One iteration of test.py:get_predictions (lines 80-93) on the fused path: (maps [B,S,S], scores [B])."""
+    return model.predict(image, epoch_text_feature, domain)

@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the AA-CLIP inference hot path on B200 (BASELINE.json: anomaly maps/s, 336 px, ViT-L/14).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch-per-gpu 64] [--impl b200|reference]
+
+A step = one pass of the hot path over one batch of synthetic images: ViT-L/14-336 visual encoder with the 6
+residual adapters, 4 taps -> ln_post -> seg/det projections -> L2 normalise -> anchor similarity -> gaussian
+blur + bilinear upsample -> level-summed 336x336 anomaly maps and image scores (test.py:80-93), through
+aaclip_forward_fused (device-resident inputs: `value`) and aaclip_forward_fused_host (pinned host buffers,
+H2D + D2H inside the timed region: `e2e`).  N > 1: one process per GPU (torchrun), batch sharded data-parallel,
+one NCCL all-gather of the image scores per step, max-over-ranks timing.
+
+--impl reference times the CPU restatement of the reference path (oracle/aaclip_oracle.py, kind "port": the
+Python reference itself cannot travel to the GPU box) on the host cores, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_IMG = 393_708_404_736          # algorithmic FLOP per image
+HEAD_BYTES_IMG = 3_993_604       # fused head algorithmic bytes per image, bf16 tokens
+METRIC = "anomaly maps/sec (336px, ViT-L-14)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--cpu-baseline-images", type=int, default=-1, help="images the CPU baseline leg runs (-1 auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_images_per_s(n_images: int, threads: int):
+    """Times the oracle (CPU restatement of the reference path) on `n_images` synthetic images, batch 1 each
+    (BASELINE.json configs[0]), after one warm-up image.  Returns (images/s, seconds)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    torch.set_num_threads(threads)
+    cfg = synth.VIT_L_14_336
+    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    T = synth.anchors(cfg, 1)
+    imgs = synth.images(n_images + 1, cfg, seed=1)
+
+    def one(i):
+        with torch.no_grad():
+            seg, det = orc.visual_forward(sd, ia, imgs[i:i + 1])
+            return orc.predict(seg, det, T, cfg.image_size, "Industrial")
+
+    one(0)
+    t0 = time.perf_counter()
+    for i in range(1, n_images + 1):
+        one(i)
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = 2  # bounded sample of the batch-64 step
+    total = per_step * (args.steps + args.warmup)
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    torch.set_num_threads(threads)
+    cfg = synth.VIT_L_14_336
+    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    T = synth.anchors(cfg, 1)
+    imgs = synth.images(per_step, cfg, seed=1)
+
+    def step():
+        with torch.no_grad():
+            seg, det = orc.visual_forward(sd, ia, imgs)
+            return orc.predict(seg, det, T, cfg.image_size, "Industrial")
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "AA-CLIP ViT-L-14-336 inference, synthetic 336x336 images, random-init weights, "
+                               "visual encoder + adapters + anomaly-map head (BASELINE.json configs[1])",
+                   "sample": f"{per_step} images per step of the batch-64 step", "device": "host CPU"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step}-image steps x {args.steps}, torch fp32 restatement of the reference path "
+                                   "(oracle/aaclip_oracle.py); the Python reference itself cannot travel to the GPU box"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from aaclip_b200 import synth
+    from aaclip_b200.dist import gather_scores, shard_range
+    from aaclip_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = synth.VIT_L_14_336
+    B = args.batch_per_gpu
+    total = B * world
+    b0, b1 = shard_range(total, rank, world)
+    assert b1 - b0 == B
+    peaks = load_peaks()
+
+    eng = Engine(cfg, device=local_rank, max_batch=B, text=False, cta_group=args.cta_group)
+    eng.load_state_dicts(synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0), None)
+    anchors = synth.anchors(cfg, 1).cuda()
+    n_rot = 4  # rotate distinct input batches: 4 x 86.7 MB > 126 MB L2, per-step activations (>1.3 GB) exceed it anyway
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    inputs = [torch.randn(B, 3, cfg.image_size, cfg.image_size, device="cuda", generator=g) for _ in range(n_rot)]
+
+    def step(i):
+        maps, scores = eng.forward_fused(inputs[i % n_rot], anchors, "Industrial")
+        if world > 1:
+            scores = gather_scores(scores, total)
+        return maps, scores
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        maps, scores = step(i)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = total * args.steps / (ms / 1e3)
+    finite = bool(torch.isfinite(maps).all() and torch.isfinite(scores).all())
+
+    # ---- per-kernel-class CUDA-event profile of the same step (2 extra steps, events around every launch)
+    eng.profile(True)
+    prof_steps = 2
+    for i in range(prof_steps):
+        eng.forward_fused(inputs[i % n_rot], anchors, "Industrial")
+    prof = eng.profile_read()
+    eng.profile(False)
+    kern = {}
+    tot_ms = sum(v[0] for v in prof.values()) / prof_steps
+    for name, (pms, cnt) in prof.items():
+        if cnt:
+            kern[name] = {"ms_per_step": pms / prof_steps, "launches_per_step": cnt // prof_steps,
+                          "share": (pms / prof_steps) / tot_ms}
+    gemm_ms = sum(v["ms_per_step"] for k, v in kern.items() if k.startswith("gemm_"))
+    gemm_launches = sum(v["launches_per_step"] for k, v in kern.items() if k.startswith("gemm_"))
+    attn_flop_img = 24 * 2 * 2 * 16 * 577 * 577 * 64
+    gemm_flop_step = (F_IMG - attn_flop_img) * B
+    gemm_tflops = gemm_flop_step / (gemm_ms / 1e3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "gemm::gemm_kernel (tcgen05, all encoder/adapter/projection GEMMs)",
+        "achieved": gemm_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": gemm_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": gemm_tflops / peaks["bf16_tflops"],
+        "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json); burst {peaks['bf16_tflops']}",
+        "flop_per_launch_avg": gemm_flop_step / max(gemm_launches, 1), "launches_per_step": gemm_launches,
+        "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / tot_ms, "traffic": None,
+        "whole_step_tflops": F_IMG * B / (ms / args.steps / 1e3) / 1e12,
+        "whole_step_frac": F_IMG * B / (ms / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
+    }
+    if "attention" in kern:
+        kern["attention"]["tflops"] = attn_flop_img * B / (kern["attention"]["ms_per_step"] / 1e3) / 1e12
+
+    # ---- e2e: same step through the host-buffer C-ABI entry (H2D of the images + D2H of maps and scores inside)
+    e2e = None
+    if not args.no_e2e:
+        S = cfg.image_size
+        h_img = [inputs[i].cpu().pin_memory() for i in range(2)]
+        h_maps = torch.empty(B, S, S).pin_memory()
+        h_scores = torch.empty(B).pin_memory()
+        h_anchor = anchors.cpu()
+        for i in range(2):
+            eng.forward_fused_host(h_img[i % 2], h_anchor, h_maps, h_scores)
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            eng.forward_fused_host(h_img[i % 2], h_anchor, h_maps, h_scores)
+            if world > 1:
+                gather_scores(h_scores.cuda(non_blocking=True), total)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total * args.steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h_img[0].numel() * 4 + h_anchor.numel() * 4),
+               "d2h_bytes_per_step": int(h_maps.numel() * 4 + h_scores.numel() * 4),
+               "api": "aaclip_forward_fused_host (C ABI, pinned host buffers, synchronous)"}
+
+    # ---- head kernel alone (HBM roofline of the fused anomaly-map head, A7 contract: 4 bf16 levels in, map out)
+    head = None
+    try:
+        from aaclip_b200 import ops
+        feats = [torch.nn.functional.normalize(torch.randn(B, cfg.patches, cfg.embed_dim, device="cuda"), dim=-1)
+                 .to(torch.bfloat16) for _ in range(4)]
+        det = torch.randn(B, cfg.embed_dim, device="cuda")
+        for _ in range(3):
+            ops.anomaly_head(feats, anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        h0.record()
+        for _ in range(reps):
+            ops.anomaly_head(feats, anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
+        h1.record()
+        torch.cuda.synchronize()
+        hms = h0.elapsed_time(h1) / reps
+        gbs = HEAD_BYTES_IMG * B / (hms / 1e3) / 1e9
+        head = {"bound": "hbm", "kernel": "patch_dots + head_maps + scores (aaclip_anomaly_head)", "achieved": gbs,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "ms": hms,
+                "images_per_s": B / (hms / 1e3), "note": "inputs 113 MB < L2: back-to-back repeats are L2-assisted"}
+    except Exception as e:  # the head microbench must never sink the headline line
+        head = {"error": str(e)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n = args.cpu_baseline_images if args.cpu_baseline_images >= 0 else 8
+        threads = os.cpu_count() or 1
+        v, secs = cpu_port_images_per_s(n, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n} images, batch 1 each (BASELINE.json configs[0]), {secs:.1f} s, torch fp32 "
+                                  "restatement of the reference path (oracle/aaclip_oracle.py)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "single B200 bf16 batch 64: ViT-L-14-336 visual encoder + residual adapters + "
+                                   "anomaly-map head producing 336x336 pixel maps and image scores (BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": total, "image_size": cfg.image_size,
+                       "parallelism": f"dp{world}", "weights": "random-init (synthetic, seed 0)",
+                       "precision": "bf16 GEMM/attention operands, fp32 accumulation, residual stream, LayerNorm, softmax, head",
+                       "l2": f"inputs rotate over {n_rot} batches ({n_rot * B * 3 * cfg.image_size ** 2 * 4 / 1e6:.0f} MB > 126 MB L2); "
+                             "per-step activation traffic (>1.3 GB) exceeds L2",
+                       "outputs_finite": finite},
+            "roofline": roofline, "roofline_head": head, "kernels": kern, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,14 @@ long long aaclip_device_bytes(const aaclip_ctx* ctx);
 /* Number of kernels the library launched on behalf of ctx since creation (for bench.py gpu_launches). */
 long long aaclip_launch_count(const aaclip_ctx* ctx);
 
+/* Optional per-launch timing: while enabled every kernel the context launches is bracketed by CUDA events on
+ * its stream.  aaclip_profile_read sums them per kernel class into ms[i] / counts[i] (i < n_classes <= 16) and
+ * clears the log.  Class order: gemm_qkv, gemm_out, gemm_fc, gemm_proj, gemm_adapter, gemm_segdet, gemm_patch,
+ * attention, layernorm, adapter_mix, cast, l2norm, det_mean, stem_misc, head_maps, other. */
+#define AACLIP_PROFILE_CLASSES 16
+int aaclip_profile_enable(aaclip_ctx* ctx, int on);
+int aaclip_profile_read(aaclip_ctx* ctx, double* ms, long long* counts, int n_classes);
+
 /* ---- AdaptedCLIP.forward (model/adapter.py:67-112) ------------------------------------------------- */
 /* image fp32 [B,3,S,S] (CLIP-normalised).  seg_out[i]: fp32 [B,P,E] L2-normalised patch tokens of level i
  * (or NULL to skip materialising them); det_out fp32 [B,E] (or NULL). */
@@ -152,6 +160,10 @@ int aaclip_forward_fused_host(aaclip_ctx* ctx, const float* host_image, int B, c
 /* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
 /* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */
 int aaclip_text_forward(aaclip_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);
+
+/* forward_utils.py:155-161: emb fp32 [n, width] (encode_text output of one prompt state) -> rows L2-normalised,
+ * averaged, re-normalised, written to column `col` (0 = normal, 1 = abnormal) of anchors fp32 [width, 2]. */
+int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int col, void* stream);
 
 /* ---- building blocks (exported so the parity tests can pin each kernel on its own) ------------------ */
 /* out = epilogue(A[M,K] . W[N,K]^T), bf16 operands (pitches lda/ldw elements), fp32 accumulation. */

@@ -1,0 +1,131 @@
+"""CPU: host logic — the C-ABI library loads and exports every symbol include/aaclip_b200.h declares, fails
+loudly without a GPU (no fallback), the drop-in module tree has the reference's state_dict keys, and the
+N>1 sharding / score gather works over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from aaclip_b200 import _lib, synth  # noqa: E402
+from aaclip_b200.dist import gather_scores, shard_range  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "aaclip_b200.h")).read()
+    declared = set(re.findall(r"\b(aaclip_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().aaclip_abi_version() == 1
+
+
+def test_cfg_struct_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "aaclip_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {"):hdr.index("} aaclip_cfg;")]
+    fields = re.findall(r"^\s*(?:int|float)\s+([a-z_]+)(?:\[\d+\])?;", body, flags=re.M)
+    assert fields == [f[0] for f in _lib.AaclipCfg._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly():
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    cfg = _lib.AaclipCfg()
+    rc = lib.aaclip_create(C.byref(ctx), C.byref(cfg), 0)
+    assert rc == -3 and b"no CPU fallback" in lib.aaclip_last_error()
+    from aaclip_b200 import ops
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    from aaclip_b200.adapter import AdaptedCLIP
+    from aaclip_b200.clip import CLIP
+    m = AdaptedCLIP(CLIP(synth.tiny_cfg(), text=False), relu=False, image_adapt_until=2, levels=[1, 2]).eval()
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(1, 3, 56, 56))
+
+
+def test_dropin_state_dict_keys_match_reference():
+    """Keys probed from the reference modules; checkpoints must load unchanged."""
+    from aaclip_b200.adapter import AdaptedCLIP
+    from aaclip_b200.clip import CLIP
+    cfg = synth.tiny_cfg()
+    for relu in (False, True):
+        m = AdaptedCLIP(CLIP(cfg), text_adapt_until=3, image_adapt_until=6, relu=relu)
+        ia = list(m.image_adapter.state_dict().keys())
+        fc = "fc.0.weight" if relu else "fc.weight"
+        assert ia == [f"layer_adapters.{i}.fc.0.weight" for i in range(6)] + \
+            [f"seg_proj.{i}.{fc}" for i in range(4)] + [f"det_proj.{fc}"]
+        assert list(m.text_adapter.state_dict().keys()) == [f"{i}.fc.0.weight" for i in range(4)]
+    # the synthetic state dicts use exactly the container's keys
+    full = synth.VIT_L_14_336
+    clip_keys = set(CLIP(synth.tiny_cfg(layers=2, t_layers=2)).state_dict().keys())
+    synth_keys = set(synth.clip_state_dict(synth.tiny_cfg(layers=2, t_layers=2)).keys())
+    assert synth_keys == clip_keys, synth_keys ^ clip_keys
+    assert synth.clip_state_dict(synth.tiny_cfg(), 0)["visual.conv1.weight"].shape == (256, 3, 14, 14)
+    assert full.tokens == 577 and full.mlp_width == 4096
+
+
+def test_weight_map_covers_hot_path():
+    from aaclip_b200.engine import weight_map
+    cfg = synth.tiny_cfg()
+    wm = weight_map(cfg)
+    keys = ["clip." + k for k in synth.clip_state_dict(cfg)] + \
+        ["image_adapter." + k for k in synth.image_adapter_state_dict(cfg)] + \
+        ["text_adapter." + k for k in synth.text_adapter_state_dict(cfg)]
+    unused = [k for k in keys if k not in wm]
+    assert sorted(unused) == ["clip.logit_scale", "clip.text_projection", "clip.visual.proj"]  # not on the path
+    assert set(wm) <= set(keys)
+    assert len({v for v in wm.values()}) == len(wm)  # (id, layer) pairs are unique
+
+
+def test_synth_is_deterministic():
+    a = synth.clip_state_dict(synth.tiny_cfg(), 0)
+    b = synth.clip_state_dict(synth.tiny_cfg(), 0)
+    c = synth.clip_state_dict(synth.tiny_cfg(), 1)
+    k = "visual.transformer.resblocks.1.mlp.c_fc.weight"
+    assert torch.equal(a[k], b[k]) and not torch.equal(a[k], c[k])
+    t = synth.tokens(5, synth.tiny_cfg())
+    assert t.dtype == torch.int32 and (t.argmax(-1) > 0).all() and (t[:, 0] == 510).all()
+
+
+@pytest.mark.parametrize("total,world", [(1024, 8), (10, 4), (3, 8), (0, 2), (64, 1)])
+def test_shard_range_partitions(total, world):
+    spans = [shard_range(total, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    sizes = [e - b for b, e in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, total, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(total, dtype=torch.float32) * 0.5 + 1
+    b, e = shard_range(total, rank, world)
+    out = gather_scores(full[b:e].clone(), total)
+    q.put((rank, bool(torch.equal(out, full))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [16, 7])
+def test_gather_scores_gloo_world2(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29611 + total
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, total, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,89 @@
+"""CPU: the oracle restatement (oracle/aaclip_oracle.py) against the golden vectors that
+oracle/make_golden.py produced by running the REAL reference modules from /root/reference.
+
+The reference ships no golden vectors of its own; these files are the pin.  Tolerance 2e-4 on
+unit-norm features / O(1) maps: the only freedom is fp32 summation order inside the BLAS the host uses.
+"""
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+import aaclip_oracle as orc  # noqa: E402
+from aaclip_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden")
+TOL = 2e-4
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    cfg = synth.VIT_L_14_336
+    return cfg, synth.clip_state_dict(cfg, 0), synth.image_adapter_state_dict(cfg, 0), synth.text_adapter_state_dict(cfg, 0)
+
+
+def test_reference_agreement_report():
+    rep = json.load(open(os.path.join(GOLD, "oracle_vs_reference.json")))
+    assert rep and all(v < TOL for v in rep.values()), rep
+
+
+def test_visual_and_head_vs_reference_golden(weights):
+    cfg, sd, ia, _ = weights
+    g = _load("visual_vitl336_b2.pt")
+    img = synth.images(g["batch"], cfg, seed=g["image_seed"])
+    T = synth.anchors(cfg, seed=g["anchor_seed"])
+    with torch.no_grad():
+        seg, det = orc.visual_forward(sd, ia, img)
+        maps_i, score = orc.predict(seg, det, T, cfg.image_size, "Industrial")
+        maps_m, _ = orc.predict(seg, det, T, cfg.image_size, "Medical")
+        train0 = orc.calculate_similarity_map(seg[0], T, cfg.image_size, test=False)
+    for s, ref in zip(seg, g["seg_sub"]):
+        assert (s[:, g["patch_idx"]] - ref).abs().max() < TOL
+    assert (det - g["det"]).abs().max() < TOL
+    assert (score - g["score"]).abs().max() < TOL
+    assert (maps_i[:, ::8, ::8] - g["map_industrial_sub"]).abs().max() < 5e-4
+    assert (maps_m[:, ::8, ::8] - g["map_medical_sub"]).abs().max() < 5e-4
+    assert (train0[:, :, ::8, ::8] - g["train_l0_sub"]).abs().max() < 5e-4
+
+
+@pytest.mark.parametrize("name", ["head_g24_s336", "head_g37_s518", "head_g16_s100"])
+def test_head_vs_reference_golden(name):
+    g = _load(name + ".pt")
+    cfg = synth.VIT_L_14_336
+    feats, Tb, det = synth.head_inputs(g["batch"], g["grid"], cfg.embed_dim, 4, seed=g["feat_seed"])
+    T = synth.anchors(cfg, seed=g["anchor_seed"])
+    for domain in ("Industrial", "Medical"):
+        m = torch.cat([orc.calculate_similarity_map(f, T, g["size"], test=True, domain=domain) for f in feats], 1).sum(1)
+        assert (m[:, ::7, ::7] - g["map_" + domain.lower()]).abs().max() < TOL
+    tr = torch.stack([orc.calculate_similarity_map(f, Tb, g["size"], test=False) for f in feats], 0)
+    assert (tr[:, :, :, ::7, ::7] - g["train_batched"]).abs().max() < TOL
+    assert (((det @ T)[:, 1] + 1) / 2 - g["score"]).abs().max() < 1e-6
+
+
+def test_text_vs_reference_golden(weights):
+    cfg, sd, _, ta = weights
+    g = _load("text_vitl336.pt")
+    with torch.no_grad():
+        emb = orc.encode_text(sd, ta, synth.tokens(6, cfg, seed=g["tok_synth_seed"]))
+        assert (emb - g["emb_synth"]).abs().max() < TOL
+        for cls, toks in g["prompt_tokens"].items():
+            a = orc.class_text_anchor(orc.encode_text(sd, ta, toks[0]), orc.encode_text(sd, ta, toks[1]))
+            assert a.shape == (768, 2)
+            assert (a - g["anchors"][cls]).abs().max() < TOL
+
+
+def test_gaussian_kernel_properties():
+    """kornia restatement ("parity unpinned"): the properties its published algorithm guarantees."""
+    for k, s in ((7, 1.0), (9, 1.5)):
+        w = orc.gaussian_kernel1d(k, s)
+        assert abs(float(w.sum()) - 1) < 1e-6 and torch.equal(w, w.flip(0)) and int(w.argmax()) == k // 2
+    x = torch.full((1, 1, 24, 24), 3.25)
+    assert (orc.gaussian_blur2d(x, (7, 7), (1.0, 1.0)) - 3.25).abs().max() < 1e-6  # constants are preserved
