@@ -157,26 +157,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
       if (causal) limit = min(limit, qi - kv0 + 1); // keys > qi are masked (CLIP text mask, model/model.py:172)
       ptx::mbar_wait(&bars->s_full, j & 1);
       ptx::tc_fence_after();
-      // ---- pass 1: row max
-      float mx = -INFINITY;
+      // ---- pass 1: row max (two 32-column TMEM loads in flight per wait, 4 independent max chains)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_s + cch * 32, v);
+      for (int cp = 0; cp < 2; ++cp) {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(t_s + cp * 64, v0);
+        ptx::tmem_ld_32x32b_x32(t_s + cp * 64 + 32, v1);
         ptx::tmem_ld_wait();
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cch * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (cp * 64 + i < limit) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
+            if (cp * 64 + 32 + i < limit) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) {
+            mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+          }
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx);
       // a fully masked row (only rows >= L of a causal tile) keeps m_new = -inf: use 0 to avoid inf - inf
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f((m - m_use) * c);
+      const float alpha = ptx::ex2_approx((m - m_use) * c);
       // ---- fold in the previous tile's P.V now that its MMA has certainly been issued
       if (j > 0) {
         ptx::mbar_wait(&bars->o_full, (j - 1) & 1);
@@ -190,35 +196,40 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __res
           for (int i = 0; i < 32; ++i) o[hh * 32 + i] = fmaf(o[hh * 32 + i], alpha_prev, __uint_as_float(v[i]));
         }
       }
-      // ---- pass 2: p = exp2((s - m) * c), bf16 P tile into swizzled smem, fp32 row sum
+      // ---- pass 2: p = exp2((s - m) * c), bf16 P tile into swizzled smem, fp32 row sum (4 chains)
       const float mc = m_use * c;
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_s + cch * 32, v);
+      for (int cp = 0; cp < 2; ++cp) {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32b_x32(t_s + cp * 64, v0);
+        ptx::tmem_ld_32x32b_x32(t_s + cp * 64 + 32, v1);
         ptx::tmem_ld_wait();
-        float p[32];
+        // keys [cp*64, cp*64+64) = swizzle atom cp: v0 -> 16-B chunks 0..3, v1 -> chunks 4..7
+        uint8_t* atom = p_row + cp * (BQ * 128);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(fmaf(__uint_as_float(v[i]), c, -mc));
-          if (need_mask && (cch * 32 + i >= limit)) e = 0.f;
-          p[i] = e;
-          rs += e;
-        }
-        // keys [cch*32, cch*32+32): swizzle atom (cch >> 1), 16-B chunks ((cch & 1) * 4 + {0..3})
-        uint8_t* atom = p_row + (cch >> 1) * (BQ * 128);
+        for (int hv = 0; hv < 2; ++hv) {
+          const uint32_t (&v)[32] = hv ? v1 : v0;
+          uint32_t pk[16];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 w;
-          w.x = ptx::pack_bf16x2(p[q4 * 8 + 0], p[q4 * 8 + 1]);
-          w.y = ptx::pack_bf16x2(p[q4 * 8 + 2], p[q4 * 8 + 3]);
-          w.z = ptx::pack_bf16x2(p[q4 * 8 + 4], p[q4 * 8 + 5]);
-          w.w = ptx::pack_bf16x2(p[q4 * 8 + 6], p[q4 * 8 + 7]);
-          const uint32_t chunk = uint32_t((cch & 1) * 4 + q4);
-          *reinterpret_cast<uint4*>(atom + ((chunk ^ sw) << 4)) = w;
+          for (int i = 0; i < 32; i += 2) {
+            float e0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), c, -mc));
+            float e1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), c, -mc));
+            if (need_mask) {
+              if (cp * 64 + hv * 32 + i >= limit) e0 = 0.f;
+              if (cp * 64 + hv * 32 + i + 1 >= limit) e1 = 0.f;
+            }
+            rs4[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = ptx::pack_bf16x2(e0, e1);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t chunk = uint32_t(hv * 4 + q4);
+            ptx::st_shared_v4(atom + ((chunk ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
         }
       }
+      const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       l = fmaf(l, alpha, rs);
       m = m_new;
       alpha_prev = alpha;

@@ -84,6 +84,24 @@ inline int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return make_tmap_bf16(tm, base, 2, dims, str, box);
 }
 
+// output tensor [rows, cols] (row pitch ld elements) of bf16 or fp32; box = 32 rows x 128 B, 128B swizzle
+inline int make_tmap_out(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, bool is_bf16) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  const uint64_t es = is_bf16 ? 2 : 4;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * es};
+  cuuint32_t box[2] = {is_bf16 ? 64u : 32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || gstr[0] % 16 != 0)
+    return fail(ERR_INVALID, "TMA output base/pitch must be 16-byte aligned");
+  CUresult r = enc(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ERR_CUDA, "cuTensorMapEncodeTiled (output) failed with CUresult %d", int(r));
+  return OK;
+}
+
 inline int sm_count(int device) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device]) return cached[device];

@@ -8,7 +8,7 @@
 namespace {
 
 template <int CG, int ACT, int OUT>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const gemm::Args& args, int num_sms,
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const gemm::Args& args, int num_sms,
                cudaStream_t stream) {
   using C = gemm::Cfg<CG>;
   auto kern = gemm::gemm_kernel<CG, ACT, OUT>;
@@ -32,16 +32,17 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const gemm::Args&
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AACLIP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args));
+  AACLIP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, args));
   return host::OK;
 }
 
 template <int CG>
-int dispatch(int act, int out_mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const gemm::Args& a, int sms,
+int dispatch(int act, int out_mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+             const gemm::Args& a, int sms,
              cudaStream_t s) {
   using namespace gemm;
 #define CASE(A_, O_) \
-  if (act == A_ && out_mode == O_) return launch_one<CG, A_, O_>(tmA, tmB, a, sms, s);
+  if (act == A_ && out_mode == O_) return launch_one<CG, A_, O_>(tmA, tmB, tmC, a, sms, s);
   CASE(ACT_NONE, OUT_BF16)
   CASE(ACT_GELU_ERF, OUT_BF16)
   CASE(ACT_QUICK_GELU, OUT_BF16)
@@ -72,10 +73,19 @@ int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N,
   if (rc) return rc;
   rc = host::make_tmap_2d(&tmB, W, N, K, ldw, cta_group == 1 ? 256 : 128);
   if (rc) return rc;
+  // output tiles leave through TMA: box = 32 rows x 128 B (64 bf16 / 32 fp32), 128B swizzle
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof tmC);
+  if (out_mode != gemm::OUT_F32_PATCH) {
+    const bool obf = (out_mode == gemm::OUT_BF16);
+    if (ldo % (obf ? 8 : 4) != 0 || ldo < N) return host::fail(host::ERR_INVALID, "gemm: output pitch %d", ldo);
+    rc = host::make_tmap_out(&tmC, out, M, N, ldo, obf);
+    if (rc) return rc;
+  }
   gemm::Args a;
   a.M = M; a.N = N; a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.pos = pos; a.P = P;
-  return cta_group == 1 ? dispatch<1>(act, out_mode, tmA, tmB, a, sms, stream)
-                        : dispatch<2>(act, out_mode, tmA, tmB, a, sms, stream);
+  return cta_group == 1 ? dispatch<1>(act, out_mode, tmA, tmB, tmC, a, sms, stream)
+                        : dispatch<2>(act, out_mode, tmA, tmB, tmC, a, sms, stream);
 }
 
 extern "C" int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,

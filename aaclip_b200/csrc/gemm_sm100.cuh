@@ -8,8 +8,11 @@
 //     computes a 256x256 tile; each CTA stages its own 128 rows of A and 128 rows of W, halving the
 //     smem/L2 operand traffic per SM.
 //   * 8 epilogue warps read TMEM with tcgen05.ld (lane == output row) and apply the fused epilogue:
-//     bias, erf-GELU / QuickGELU / LeakyReLU, bf16 or fp32 store, in-place fp32 residual add, or the
-//     patch-embedding scatter (+positional embedding).
+//     bias, erf-GELU / QuickGELU / LeakyReLU.  Results are staged per warp in 128B-swizzled smem (32 rows x
+//     128 B, bank-conflict free) and leave the SM as TMA tile stores (cp.async.bulk.tensor) or, for the fp32
+//     residual stream, TMA reduce-adds (cp.reduce.async.bulk.tensor .add): x += tile happens in L2, the SM
+//     never reads x, every global access is a full 128 B line, and ragged M/N tails are clipped by the TMA
+//     unit.  The tiny patch-embedding GEMM keeps a direct register->global scatter (+positional embedding).
 //
 // These replace the cuBLAS/cuDNN + ATen elementwise call sites of the reference:
 //   in_proj / out_proj   model/transformer.py:237 (nn.MultiheadAttention)      -> ACT_NONE + OUT_BF16 / OUT_F32_RESID
@@ -48,28 +51,33 @@ struct Cfg {
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int NUM_EPI_WARPS = 8;
+  static constexpr int STAGING_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int THREADS = 128 + NUM_EPI_WARPS * 32;
   static constexpr int TMEM_COLS = 512;    // 2 accumulator buffers x 256 fp32 columns
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + ~10 FMA, branch free.
+// erf-GELU via Abramowitz-Stegun 7.1.26 (|erf err| <= 1.5e-7): 0.5x(1+erf(x/sqrt2)) = hx + |hx| * erf(|x|/sqrt2),
+// erf(z) = 1 - t(a1 + t(a2 + t(a3 + t(a4 + t a5)))) exp(-z^2), t = 1/(1 + p z).  Branch free: one MUFU.RCP, one
+// MUFU.EX2 and 11 FMA-pipe instructions per element (constants pre-folded onto x).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float ax = fabsf(x);
+  const float t = ptx::rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float e = ptx::ex2_approx((x * x) * (-0.5f * 1.4426950408889634f));   // exp(-x^2/2)
   const float erf_abs = fmaf(-p, e, 1.0f);
   const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);  // 0.5x(1+erf(x/sqrt2)); sign(x)*erf_abs folded into |hx|
+  return fmaf(fabsf(hx), erf_abs, hx);
 }
+// x * sigmoid(1.702 x)  (model/transformer.py:46-49)
 __device__ __forceinline__ float quick_gelu(float x) {
-  return x * __frcp_rn(1.0f + exp2f(-1.702f * 1.4426950408889634f * x));
+  return x * ptx::rcp_approx(1.0f + ptx::ex2_approx(-1.702f * 1.4426950408889634f * x));
 }
 
 template <int ACT>
@@ -136,16 +144,89 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
   }
 }
 
+// bias + activation on 32 accumulator columns
+template <int ACT>
+__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], float (&f)[32], const float* bias, int col) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT>(f[j]);
+}
+
+// One epilogue warp drains its 32 rows x 128 accumulator columns: TMEM -> regs -> swizzled smem -> TMA.
+// `stage` is this warp's private 4 KB buffer; lane == row.  Lane 0 owns the bulk async-groups.
+template <int ACT, int OUT, typename ArriveFn>
+__device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage, const CUtensorMap* tmC, int row0,
+                                                int col0, uint32_t lane, const Args& a, ArriveFn&& release_tmem) {
+  uint8_t* my_row = stage + lane * 128;
+  const uint32_t sw = lane & 7u;
+  constexpr int COLS_PER_STORE = (OUT == OUT_BF16) ? 64 : 32;   // 128 B per row either way
+  constexpr int N_STORES = 128 / COLS_PER_STORE;
+#pragma unroll 1
+  for (int c = 0; c < N_STORES; ++c) {
+    const int col = col0 + c * COLS_PER_STORE;
+    uint32_t w[32];  // 128 B of output for this row
+    if constexpr (OUT == OUT_BF16) {
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32b_x32(t_addr + c * 64, v0);
+      ptx::tmem_ld_32x32b_x32(t_addr + c * 64 + 32, v1);
+      ptx::tmem_ld_wait();
+      if (c == N_STORES - 1) release_tmem();
+      float f[32];
+      bias_act32<ACT>(v0, f, a.bias, col);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = ptx::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+      bias_act32<ACT>(v1, f, a.bias, col + 32);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[16 + j] = ptx::pack_bf16x2(f[2 * j], f[2 * j + 1]);
+    } else {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
+      ptx::tmem_ld_wait();
+      if (c == N_STORES - 1) release_tmem();
+      float f[32];
+      bias_act32<ACT>(v, f, a.bias, col);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
+    }
+    // the previous TMA store out of this buffer must have finished reading it
+    if (lane == 0) ptx::bulk_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      ptx::st_shared_v4(my_row + ((uint32_t(q) ^ sw) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (col < a.N && row0 < a.M) {
+        if constexpr (OUT == OUT_F32_RESID) ptx::tma_reduce_add_2d(tmC, stage, col, row0);
+        else ptx::tma_store_2d(tmC, stage, col, row0);
+      }
+      ptx::bulk_commit();
+    }
+  }
+}
+
 template <int CG, int ACT, int OUT>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args args) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const Args args) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // identical offset in both CTAs of a pair: the dynamic smem window starts at the same address
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::NUM_EPI_WARPS * C::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
@@ -167,6 +248,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if constexpr (OUT != OUT_F32_PATCH) ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1 && ptx::elect_one()) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -242,32 +324,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue: TMEM -> regs -> global
+    // ===================================================== epilogue: TMEM -> regs -> (smem -> TMA | global)
     const uint32_t q = warp & 3u;            // TMEM lane quarter this warp may read
     const uint32_t half = (warp - 4u) >> 2;  // which 128 accumulator columns
+    uint8_t* stage = staging + (warp - 4u) * C::STAGING_BYTES;
     uint32_t it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
-      const int row = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u + lane);
+      const int row0 = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * C::BN + half * 128u;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (c == 3) {
-          // every TMEM read of this accumulator buffer is done: hand it back to the MMA warp
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 1) ptx::mbar_arrive(&tempty[acc]); else ptx::mbar_arrive_cluster(&tempty[acc], 0);
-          }
+      // every TMEM read of this accumulator buffer is done: hand it back to the MMA warp
+      auto release_tmem = [&]() {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1) ptx::mbar_arrive(&tempty[acc]); else ptx::mbar_arrive_cluster(&tempty[acc], 0);
         }
-        epilogue_chunk<ACT, OUT>(v, row, n_blk * C::BN + int(half) * 128 + c * 32, args);
+      };
+      if constexpr (OUT == OUT_F32_PATCH) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (c == 3) release_tmem();
+          epilogue_chunk<ACT, OUT>(v, row0 + int(lane), n_blk * C::BN + int(half) * 128 + c * 32, args);
+        }
+      } else {
+        epilogue_staged<ACT, OUT>(t_addr, stage, &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args,
+                                  release_tmem);
       }
+    }
+    if constexpr (OUT != OUT_F32_PATCH) {
+      if (lane == 0) ptx::bulk_wait<0>();  // smem must outlive the last TMA store's read; writes are done too
     }
   }
 
