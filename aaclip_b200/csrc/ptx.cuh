@@ -63,22 +63,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) elapses, so a
+// waiting role (TMA producer, MMA issuer) costs almost no issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never
-// as a hung GPU.  ~4e9 cycles is seconds; no legitimate wait in these kernels is close to that.
+// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung
+// GPU.  The bound is on retries (each retry sleeps in hardware), far beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { __trap(); }
+    if (++tries > 50000000u) { __trap(); }
   }
 }
 
