@@ -65,6 +65,7 @@ SIGNATURES = {
     "aaclip_gemm_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "aaclip_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "aaclip_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "aaclip_attention_trace": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "aaclip_adapter_mix": (_i, [_vp, _vp, _f, _i, _i, _vp]),
 }
 

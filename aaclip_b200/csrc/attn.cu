@@ -10,9 +10,14 @@
 //               TMEM accumulator, O_j = P_j V_j (M128 N64 K64) into a second double-buffered accumulator
 //   warps 0..3  softmax, thread == query row: ONE tcgen05.ld of the 64 scores of the tile into registers,
 //               row max (FMNMX3 chains), exp2 on the SFU, fp32 row sum, P_j written as bf16 into
-//               128B-swizzled smem (the A operand of the PV MMA).  O is accumulated in registers with the
-//               online-softmax rescale; the fold of O_{j-1} runs after P_j has been handed to the tensor
-//               core, so it overlaps the PV_j / S_{j+2} MMAs.
+//               128B-swizzled, double-buffered smem (the A operand of the PV MMA).
+// O never leaves TMEM during the key loop: PV_j accumulates into it (tcgen05.mma accumulate), and the
+// online-softmax rescale is LAZY - the row keeps exponentiating against a stale max until the true max has
+// grown by more than 2^8, only then is O read (tcgen05.ld), scaled and written back (tcgen05.st).  Softmax
+// is shift invariant, so the result is unchanged; P entries are bounded by 256, which bf16 holds with the
+// same relative precision.  The softmax warps are therefore pure SFU streams (the kernel's real bound:
+// one exp2 per score on 16 SFU lanes/SM) and never wait on the tensor core in steady state
+// (tools/attn_trace.py records the per-tile timeline).
 // S_{j+1} is always computed while the softmax warps work on S_j, so they never wait for the tensor core
 // in steady state.  Operands come straight out of the fused QKV GEMM output qkv[B*L, 3*heads*64] through
 // 2-D tensor maps: rows past the image's last token are either the next image's tokens or TMA zero fill
@@ -20,6 +25,7 @@
 // The ragged last key tile (577 = 9*64 + 1) only pays for the 32-key group(s) that hold valid keys: the
 // softmax skips fully masked 32-column groups and the PV MMA shortens its K extent.
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "internal.h"
 #include "ptx.cuh"
@@ -35,23 +41,24 @@ constexpr int Q_BYTES = BQ * D * 2;      // 16 KB
 constexpr int KV_BYTES = BKV * D * 2;    //  8 KB
 constexpr int P_BYTES = BQ * BKV * 2;    // 16 KB: one 128B-swizzle atom column (64 keys) x 128 rows
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;           // S0 [0,64) S1 [64,128) O0 [128,192) O1 [192,256)
+constexpr int TMEM_COLS = 256;           // S0 [0,64) S1 [64,128) O [128,192)
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + Q_BYTES;
 constexpr int OFF_V = OFF_K + NST * KV_BYTES;
 constexpr int OFF_P = OFF_V + NST * KV_BYTES;
-constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;       // P is double buffered: P_j is written while PV_{j-1} still reads
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 
 struct Bars {
-  uint64_t q_full, k_full[NST], v_full[NST], k_empty[NST], v_empty[NST], s_full[2], p_full, o_full;
+  uint64_t q_full, k_full[NST], v_full[NST], k_empty[NST], v_empty[NST], s_full[2], p_free[2], p_full[2];
   uint32_t tmem_slot;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
 __global__ void __launch_bounds__(THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                 __nv_bfloat16* __restrict__ out, int L, int heads, int causal) {
+                 __nv_bfloat16* __restrict__ out, int L, int heads, int causal, long long* trace, int trace_cta,
+                 float rescale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-B alignment
   Bars* bars = reinterpret_cast<Bars*>(smem + OFF_BAR);
@@ -64,6 +71,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (causal) kv_end = min(L, q0 + BQ);
   const int n_kv = (kv_end + BKV - 1) / BKV;
   const int row_base = b * L;  // first token row of this image in qkv / out
+  // optional clock64 trace of one CTA (diagnostics): [0..15][tile] softmax warp 0, [16..23][tile] MMA thread
+  const int cta_linear = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const bool tracing = (trace != nullptr) && (cta_linear == trace_cta);
+#define TRACE(slot, tile) do { if (tracing) trace[(slot) * 16 + (tile)] = clock64(); } while (0)
 
   if (warp == 5 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQ);
@@ -77,8 +88,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     ptx::mbar_init(&bars->s_full[0], 1);
     ptx::mbar_init(&bars->s_full[1], 1);
-    ptx::mbar_init(&bars->p_full, 4);  // one arrive per softmax warp
-    ptx::mbar_init(&bars->o_full, 1);
+    ptx::mbar_init(&bars->p_free[0], 1);
+    ptx::mbar_init(&bars->p_free[1], 1);
+    // one arrive per softmax warp.  Two alternating barriers: a fast warp may hand in P_{j+1} before a slow
+    // warp has handed in P_j (nothing else orders them), and two arrivals must never land in one phase.
+    ptx::mbar_init(&bars->p_full[0], 4);
+    ptx::mbar_init(&bars->p_full[1], 4);
     ptx::fence_barrier_init();
   }
   if (warp == 4) {
@@ -111,42 +126,60 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(BQ, BKV, 0, 0);  // Q K-major, K K-major
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32(BQ, D, 0, 1);    // P K-major, V MN-major
-      const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
-      const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
-      auto issue_s = [&](int j) {   // S_j -> TMEM S[j & 1]
-        const int st = j % NST;
-        ptx::mbar_wait(&bars->k_full[st], (j / NST) & 1);
+      // smem matrix descriptors: constant high word (SBO 1024 B, version 1, SWIZZLE_128B), low word = addr >> 4
+      // (| LBO field); stepping a tile / a 16-element K slice is an integer add on the low word.
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      auto desc = [](uint32_t lo) { return (uint64_t(DESC_HI) << 32) | lo; };
+      const uint32_t q_lo = ((ptx::smem_u32(smem + OFF_Q) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t k_lo = ((ptx::smem_u32(smem + OFF_K) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t p_lo = ((ptx::smem_u32(smem + OFF_P) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t v_lo = ((ptx::smem_u32(smem + OFF_V) & 0x3FFFFu) >> 4) | ((1024u >> 4) << 16);
+      int s_j = 0, s_st = 0; uint32_t s_ph = 0;     // next S tile to issue and its K ring slot / phase
+      auto issue_s = [&]() {   // S_{s_j} -> TMEM S[s_j & 1]
+        ptx::mbar_wait(&bars->k_full[s_st], s_ph);
         ptx::tc_fence_after();
-        const uint32_t k_addr = ptx::smem_u32(smem + OFF_K + st * KV_BYTES);
-        const uint32_t t_s = tmem_base + uint32_t(j & 1) * 64u;
+        const uint32_t kb = k_lo + uint32_t(s_st) * (KV_BYTES >> 4);
+        const uint32_t t_s = tmem_base + uint32_t(s_j & 1) * 64u;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          ptx::mma_f16_ss<1>(t_s, ptx::umma_desc_kmajor_sw128(q_addr + k * 32),
-                             ptx::umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-        ptx::mma_commit(&bars->s_full[j & 1]);
-        ptx::mma_commit(&bars->k_empty[st]);
+          ptx::mma_f16_ss<1>(t_s, desc(q_lo + k * 2), desc(kb + k * 2), idesc_s, k != 0 ? 1u : 0u);
+        ptx::mma_commit(&bars->s_full[s_j & 1]);
+        ptx::mma_commit(&bars->k_empty[s_st]);
+        ++s_j;
+        if (++s_st == NST) { s_st = 0; s_ph ^= 1u; }
       };
       ptx::mbar_wait(&bars->q_full, 0);
-      issue_s(0);
-      if (n_kv > 1) issue_s(1);
+      issue_s();
+      if (n_kv > 1) issue_s();
+      int st = 0; uint32_t ph = 0;
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j % NST;
-        ptx::mbar_wait(&bars->p_full, j & 1);  // P_j in smem, S[j&1] drained into registers, O[(j+1)&1] folded
-        ptx::mbar_wait(&bars->v_full[st], (j / NST) & 1);
+        TRACE(16, j);
+        ptx::mbar_wait(&bars->p_full[j & 1], (j >> 1) & 1);  // P_j in smem, S[j&1] drained, O rescaled if needed
+        TRACE(17, j);
+        ptx::mbar_wait(&bars->v_full[st], ph);
         ptx::tc_fence_after();
-        const uint32_t v_addr = ptx::smem_u32(smem + OFF_V + st * KV_BYTES);
-        const uint32_t t_o = tmem_base + 128u + uint32_t(j & 1) * 64u;
-        const int keys = min(BKV, kv_end - j * BKV);
-        const int ksteps = (keys + 15) >> 4;       // ragged last tile: skip 16-key groups that are fully masked
-        for (int k = 0; k < ksteps; ++k) {
-          // A: P tile = one 64-key swizzle atom column (128 rows x 128 B); B: 16 keys = 16 rows x 128 B of V
-          const uint64_t ad = ptx::umma_desc_kmajor_sw128(p_addr + k * 32);
-          const uint64_t bd = ptx::umma_desc_mnmajor_sw128(v_addr + k * 16 * 128, 1024);
-          ptx::mma_f16_ss<1>(t_o, ad, bd, idesc_o, k != 0 ? 1u : 0u);
+        TRACE(18, j);
+        const uint32_t pb = p_lo + uint32_t(j & 1) * (P_BYTES >> 4);
+        const uint32_t vb = v_lo + uint32_t(st) * (KV_BYTES >> 4);
+        const uint32_t t_o = tmem_base + 128u;
+        const uint32_t acc0 = j > 0 ? 1u : 0u;   // O accumulates over key tiles
+        // A: P tile = one 64-key swizzle atom column (128 rows x 128 B), 16 keys = +32 B;
+        // B: V tile as TMA landed it (MN-major), 16 keys = 16 rows x 128 B = +2048 B
+        if (j + 1 < n_kv || kv_end - j * BKV >= BKV) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)
+            ptx::mma_f16_ss<1>(t_o, desc(pb + k * 2), desc(vb + k * 128), idesc_o, k != 0 ? 1u : acc0);
+        } else {   // ragged last tile: skip 16-key groups that are fully hidden
+          const int ksteps = (kv_end - j * BKV + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            ptx::mma_f16_ss<1>(t_o, desc(pb + k * 2), desc(vb + k * 128), idesc_o, k != 0 ? 1u : acc0);
         }
-        ptx::mma_commit(&bars->o_full);
         ptx::mma_commit(&bars->v_empty[st]);
-        if (j + 2 < n_kv) issue_s(j + 2);
+        ptx::mma_commit(&bars->p_free[j & 1]);   // PV_j has landed in O and has finished reading P[j & 1]
+        if (++st == NST) { st = 0; ph ^= 1u; }
+        TRACE(19, j);
+        if (s_j < n_kv) issue_s();
+        TRACE(20, j);
       }
     }
   } else {
@@ -154,27 +187,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t quarter = warp & 3u;
     const int row = int(quarter * 32u + lane);
     const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16);
+    const uint32_t t_o = t_lane + 128u;
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const float RESCALE_LOG2 = rescale_log2;       // lazy rescale: tolerate p up to 2^8 before touching O
     uint8_t* p_row = smem + OFF_P + row * 128;
     const uint32_t sw = uint32_t(row & 7);
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float m_used = 0.f, l = 0.f;                   // stabiliser in use (<= true running max), row sum
     const int qi = q0 + row;
-
-    // o = o * alpha_prev + O_{jj}  (TMEM buffer jj & 1)
-    auto fold_o = [&](int jj) {
-      const uint32_t t_o = t_lane + 128u + uint32_t(jj & 1) * 64u;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_o + hh * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[hh * 32 + i] = fmaf(o[hh * 32 + i], alpha_prev, __uint_as_float(v[i]));
-      }
-    };
 
     for (int j = 0; j < n_kv; ++j) {
       const int kv0 = j * BKV;
@@ -184,8 +203,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int tile_keys = min(BKV, kv_end - kv0);   // warp-uniform: keys any row of the tile may see
       const bool two_halves = tile_keys > 32;
 
+      const bool tr = tracing && warp == 0 && lane == 0;
+#define TRS(slot) do { if (tr) trace[(slot) * 16 + j] = clock64(); } while (0)
+      TRS(0);
       ptx::mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);
       ptx::tc_fence_after();
+      TRS(1);
       uint32_t sv[64];
       {
         const uint32_t t_s = t_lane + uint32_t(j & 1) * 64u;
@@ -195,12 +218,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (two_halves) ptx::tmem_ld_32x32b_x32(t_s + 32, hi);
         ptx::tmem_ld_wait();
       }
+      TRS(2);
       if (need_mask) {   // rare path (last key tile / causal diagonal): hidden keys -> -inf -> p = 0
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= limit) sv[i] = 0xff800000u;
       }
-      // ---- row max: 4 independent chains (FMNMX3)
+      // ---- row max of the tile: 4 independent chains (FMNMX3)
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < 32; i += 2)
@@ -210,11 +234,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int i = 32; i < 64; i += 2)
           mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
       }
-      const float m_new = fmaxf(m, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
-      // a fully hidden row (only rows >= L, never stored) keeps m_new = -inf: use 0 to avoid inf - inf
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ptx::ex2_approx((m - m_use) * c);
-      const float mc = m_use * c;
+      const float mt = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // ---- stabiliser: first tile adopts its max; later tiles only when the max grew by more than 2^8
+      if (j == 0) {
+        m_used = (mt == -INFINITY) ? 0.f : mt;      // a fully hidden row (rows >= L, never stored) uses 0
+      } else {
+        const bool grow = (mt - m_used) * c > RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, grow)) {          // warp-uniform: tcgen05.ld/st are warp-collective
+          const float m_next = grow ? mt : m_used;
+          const float alpha = ptx::ex2_approx((m_used - m_next) * c);   // 1 for rows that keep their max
+          // PV_{j-1} has landed in O.  p_free[b] is waited at every use of buffer b, so this thread is never
+          // more than one phase behind it (an mbarrier parity wait cannot tell phase k from phase k+2; a
+          // barrier that is only waited on occasionally - the old o_full - silently aliases).
+          ptx::mbar_wait(&bars->p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_o + hh * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            ptx::tmem_st_32x32b_x32(t_o + hh * 32, v);
+          }
+          ptx::tmem_st_wait();
+          l *= alpha;
+          m_used = m_next;
+        }
+      }
+      const float mc = m_used * c;
       // ---- p = exp2((s - m) * c) as packed bf16 pairs, fp32 row sum (4 chains)
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
@@ -234,46 +282,52 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           pk[i >> 1] = ptx::pack_bf16x2(e0, e1);
         }
       }
-      // ---- P_j -> smem once PV_{j-1} has finished reading P_{j-1}
-      if (j > 0) {
-        ptx::mbar_wait(&bars->o_full, (j - 1) & 1);
-        ptx::tc_fence_after();
-      }
+      l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      TRS(3);
+      // ---- P_j -> smem buffer j & 1 once its previous reader PV_{j-2} is done (two tiles ago: no stall).
+      //      p_free[b] completes once per use of buffer b, so use number (j >> 1) - 1 is always the current
+      //      or the immediately preceding phase (mbarrier parity waits cannot look further back).
+      if (j > 1) ptx::mbar_wait(&bars->p_free[j & 1], ((j >> 1) - 1) & 1);
+      TRS(4);
+      uint8_t* pr = p_row + (j & 1) * P_BYTES;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4)
-        ptx::st_shared_v4(p_row + ((uint32_t(q4) ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2],
+        ptx::st_shared_v4(pr + ((uint32_t(q4) ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2],
                           pk[4 * q4 + 3]);
       if (two_halves) {
 #pragma unroll
         for (int q4 = 4; q4 < 8; ++q4)
-          ptx::st_shared_v4(p_row + ((uint32_t(q4) ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2],
+          ptx::st_shared_v4(pr + ((uint32_t(q4) ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2],
                             pk[4 * q4 + 3]);
       }
+      TRS(5);
       ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars->p_full);
-      // ---- fold O_{j-1} while the tensor core runs PV_j
-      if (j > 0) fold_o(j - 1);
-      l = fmaf(l, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      m = m_new;
-      alpha_prev = alpha;
+      if (lane == 0) ptx::mbar_arrive(&bars->p_full[j & 1]);
+      TRS(6);
     }
-    // ---- last tile's P.V
-    ptx::mbar_wait(&bars->o_full, (n_kv - 1) & 1);
+    // ---- O is complete once the last PV has landed: normalise by the row sum and store
+    ptx::mbar_wait(&bars->p_free[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     ptx::tc_fence_after();
-    fold_o(n_kv - 1);
-    if (qi < L) {
-      const float inv = 1.0f / l;
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row_base + qi) * W + h * D);
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = out + (size_t)(row_base + qi) * W + h * D;
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        uint4 w;
-        w.x = ptx::pack_bf16x2(o[q4 * 8 + 0] * inv, o[q4 * 8 + 1] * inv);
-        w.y = ptx::pack_bf16x2(o[q4 * 8 + 2] * inv, o[q4 * 8 + 3] * inv);
-        w.z = ptx::pack_bf16x2(o[q4 * 8 + 4] * inv, o[q4 * 8 + 5] * inv);
-        w.w = ptx::pack_bf16x2(o[q4 * 8 + 6] * inv, o[q4 * 8 + 7] * inv);
-        dst[q4] = w;
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(t_o + hh * 32, v);
+      ptx::tmem_ld_wait();
+      if (qi < L) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + hh * 32);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 w;
+          w.x = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]) * inv, __uint_as_float(v[q4 * 8 + 1]) * inv);
+          w.y = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]) * inv, __uint_as_float(v[q4 * 8 + 3]) * inv);
+          w.z = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]) * inv, __uint_as_float(v[q4 * 8 + 5]) * inv);
+          w.w = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]) * inv, __uint_as_float(v[q4 * 8 + 7]) * inv);
+          dst[q4] = w;
+        }
       }
     }
   }
@@ -286,6 +340,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace attn
 
+namespace {
+long long* g_trace = nullptr;   // diagnostics only (aaclip_attention_trace)
+int g_trace_cta = -1;
+}
+
 int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int causal, cudaStream_t stream) {
   if (B <= 0) return host::OK;
   if (L <= 0 || heads <= 0) return host::fail(host::ERR_INVALID, "attention: L=%d heads=%d", L, heads);
@@ -296,18 +355,33 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   rc = host::make_tmap_2d(&tmKV, qkv, (uint64_t)B * L, 3 * W, 3 * W, attn::BKV);
   if (rc) return rc;
   static bool configured = false;
+  static int smem_bytes = attn::SMEM_BYTES;
   if (!configured) {
+    // diagnostics: AACLIP_ATTN_PAD_SMEM=<bytes> pads the dynamic smem request (forces 1 CTA/SM for experiments)
+    if (getenv("AACLIP_ATTN_PAD_SMEM")) smem_bytes += atoi(getenv("AACLIP_ATTN_PAD_SMEM"));
     AACLIP_CUDA_CHECK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           attn::SMEM_BYTES));
+                                           smem_bytes));
     configured = true;
   }
   dim3 grid((L + attn::BQ - 1) / attn::BQ, heads, B);
-  attn::attention_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(
-      tmQ, tmKV, static_cast<__nv_bfloat16*>(out), L, heads, causal);
+  attn::attention_kernel<<<grid, attn::THREADS, smem_bytes, stream>>>(
+      tmQ, tmKV, static_cast<__nv_bfloat16*>(out), L, heads, causal, g_trace, g_trace_cta,
+      getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f);
   AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }
 
 extern "C" int aaclip_attention(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream) {
   return k::launch_attention(qkv, out, B, L, heads, causal, static_cast<cudaStream_t>(stream));
+}
+
+// Diagnostics: like aaclip_attention, but CTA number `cta` also records clock64() stamps of its softmax warp 0
+// (slots 0..7) and of its MMA-issuing thread (slots 16..20) per key tile into trace[slot * 16 + tile] (device
+// memory, >= 24 * 16 int64).  Used to study the pipeline; not part of the hot path.
+extern "C" int aaclip_attention_trace(const void* qkv, void* out, int B, int L, int heads, int causal, long long* trace,
+                                      int cta, void* stream) {
+  g_trace = trace; g_trace_cta = cta;
+  int rc = k::launch_attention(qkv, out, B, L, heads, causal, static_cast<cudaStream_t>(stream));
+  g_trace = nullptr; g_trace_cta = -1;
+  return rc;
 }

@@ -175,6 +175,10 @@ int aaclip_layernorm(const float* x, const float* gamma, const float* beta, floa
 /* softmax(q k^T / 8) v per head, head dim 64 (nn.MultiheadAttention core, model/transformer.py:237);
  * qkv bf16 [B*L, 3*heads*64], out bf16 [B*L, heads*64]; causal != 0 applies CLIP's text mask (model/model.py:172). */
 int aaclip_attention(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream);
+/* Diagnostics: aaclip_attention + clock64() stamps of CTA `cta` (softmax warp 0: slots 0..7, MMA thread: slots
+ * 16..20) per key tile into trace[slot*16 + tile] (device int64[24*16]). */
+int aaclip_attention_trace(const void* qkv, void* out, int B, int L, int heads, int causal, long long* trace, int cta,
+                           void* stream);
 /* adapter mix x <- w*a*||x||/||a|| + (1-w)*x (model/adapter.py:93-99) */
 int aaclip_adapter_mix(float* x, const float* a, float w, int rows, int width, void* stream);
 
