@@ -35,7 +35,7 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch-per-gpu", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -215,13 +215,14 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
     for i in range(args.steps):
         maps, scores = step(i)
-    ev1.record()
+        evs[i + 1].record()
     sync_all()
-    ms = ev0.elapsed_time(ev1)
+    ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
     t = torch.tensor([ms], device="cuda")
     if world > 1:
@@ -313,7 +314,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = args.cpu_baseline_images if args.cpu_baseline_images >= 0 else 8
+        n = args.cpu_baseline_images if args.cpu_baseline_images >= 0 else 48
         threads = os.cpu_count() or 1
         v, secs = cpu_port_images_per_s(n, threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -335,6 +336,7 @@ def main():
                        "outputs_finite": finite},
             "roofline": roofline, "roofline_head": head, "kernels": kern, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
+            "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
