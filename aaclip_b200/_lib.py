@@ -56,6 +56,7 @@ SIGNATURES = {
     "aaclip_launch_count": (_ll, [_vp]),
     "aaclip_profile_enable": (_i, [_vp, _i]),
     "aaclip_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll), _i]),
+    "aaclip_profile_span_ms": (C.c_double, [_vp]),
     "aaclip_visual_forward": (_i, [_vp, _vp, _i, C.POINTER(_vp), _vp, _vp]),
     "aaclip_anomaly_head": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "aaclip_forward_fused": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),

@@ -55,6 +55,7 @@ struct Bars {
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
+template <bool TRACE_ON, int POLY>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  __nv_bfloat16* __restrict__ out, int L, int heads, int causal, long long* trace, int trace_cta,
@@ -73,8 +74,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int row_base = b * L;  // first token row of this image in qkv / out
   // optional clock64 trace of one CTA (diagnostics): [0..15][tile] softmax warp 0, [16..23][tile] MMA thread
   const int cta_linear = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  const bool tracing = (trace != nullptr) && (cta_linear == trace_cta);
-#define TRACE(slot, tile) do { if (tracing) trace[(slot) * 16 + (tile)] = clock64(); } while (0)
+  const bool tracing = TRACE_ON && (trace != nullptr) && (cta_linear == trace_cta);
+#define TRACE(slot, tile) do { if (TRACE_ON && tracing) trace[(slot) * 16 + (tile)] = clock64(); } while (0)
 
   if (warp == 5 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQ);
@@ -192,60 +193,97 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float RESCALE_LOG2 = rescale_log2;       // lazy rescale: tolerate p up to 2^8 before touching O
     uint8_t* p_row = smem + OFF_P + row * 128;
     const uint32_t sw = uint32_t(row & 7);
-    float m_used = 0.f, l = 0.f;                   // stabiliser in use (<= true running max), row sum
+    float m_used = 0.f, l = 0.f;                   // stabiliser in use (<= true running max + 2^8), row sum
     const int qi = q0 + row;
+    uint32_t sv[64];                               // raw scores of the current tile (this thread's row)
+    uint32_t (&sv_lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
+    uint32_t (&sv_hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
 
-    for (int j = 0; j < n_kv; ++j) {
+    // tile geometry (warp-uniform except `limit`)
+    auto tile_keys_of = [&](int j) { return min(BKV, kv_end - j * BKV); };   // keys any row of the tile may see
+    // issue the TMEM loads of S_j (no wait): 32 or 64 columns depending on how many keys the tile holds
+    auto load_scores = [&](int j) {
+      const uint32_t t_s = t_lane + uint32_t(j & 1) * 64u;
+      ptx::tmem_ld_32x32b_x32(t_s, sv_lo);
+      if (tile_keys_of(j) > 32) ptx::tmem_ld_32x32b_x32(t_s + 32, sv_hi);
+    };
+    // hidden keys -> -inf -> p = 0 (last key tile / causal diagonal only)
+    auto mask_scores = [&](int j) {
       const int kv0 = j * BKV;
-      const bool need_mask = (kv0 + BKV > L) || (causal && kv0 + BKV > q0 + 1);
-      int limit = L - kv0;                            // this row sees keys [0, limit) of the tile
-      if (causal) limit = min(limit, qi - kv0 + 1);   // CLIP text mask (model/model.py:172): keys > qi hidden
-      const int tile_keys = min(BKV, kv_end - kv0);   // warp-uniform: keys any row of the tile may see
-      const bool two_halves = tile_keys > 32;
-
-      const bool tr = tracing && warp == 0 && lane == 0;
-#define TRS(slot) do { if (tr) trace[(slot) * 16 + j] = clock64(); } while (0)
-      TRS(0);
-      ptx::mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);
-      ptx::tc_fence_after();
-      TRS(1);
-      uint32_t sv[64];
-      {
-        const uint32_t t_s = t_lane + uint32_t(j & 1) * 64u;
-        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
-        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
-        ptx::tmem_ld_32x32b_x32(t_s, lo);
-        if (two_halves) ptx::tmem_ld_32x32b_x32(t_s + 32, hi);
-        ptx::tmem_ld_wait();
-      }
-      TRS(2);
-      if (need_mask) {   // rare path (last key tile / causal diagonal): hidden keys -> -inf -> p = 0
+      if ((kv0 + BKV > L) || (causal && kv0 + BKV > q0 + 1)) {
+        int limit = L - kv0;                            // this row sees keys [0, limit) of the tile
+        if (causal) limit = min(limit, qi - kv0 + 1);   // CLIP text mask (model/model.py:172): keys > qi hidden
 #pragma unroll
         for (int i = 0; i < 64; ++i)
           if (i >= limit) sv[i] = 0xff800000u;
       }
-      // ---- row max of the tile: 4 independent chains (FMNMX3)
+    };
+    // One streaming pass over the tile: p = exp2((s - m) * c) -> bf16 -> swizzled smem (16 B per 8 keys, stored as
+    // soon as packed), fp32 row sum and the tile's row max, all in one instruction stream so that the FMNMX /
+    // FADD / F2FP / STS work hides under the SFU (MUFU.EX2) latency instead of forming serial phases.
+    // POLY of every 8 exponentials are evaluated on the FMA pipe (Cody-Waite + cubic) to unload the SFU.
+    auto exp_pass = [&](uint8_t* pr, float mc, int n_groups, float& rowsum, float& rowmax) {
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 32; i += 2)
-        mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
-      if (two_halves) {
+      for (int g = 0; g < 8; ++g) {
+        if (g < n_groups) {
+          float e[8];
 #pragma unroll
-        for (int i = 32; i < 64; i += 2)
-          mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+          for (int i = 0; i < 8; ++i) {
+            const float x = fmaf(__uint_as_float(sv[8 * g + i]), c, -mc);
+            e[i] = (i >= 8 - POLY) ? ptx::ex2_poly3(x) : ptx::ex2_approx(x);
+          }
+          mx4[g & 3] = fmaxf(mx4[g & 3], fmaxf(fmaxf(__uint_as_float(sv[8 * g + 0]), __uint_as_float(sv[8 * g + 1])),
+                                               fmaxf(__uint_as_float(sv[8 * g + 2]), __uint_as_float(sv[8 * g + 3]))));
+          mx4[(g + 2) & 3] = fmaxf(mx4[(g + 2) & 3],
+                                   fmaxf(fmaxf(__uint_as_float(sv[8 * g + 4]), __uint_as_float(sv[8 * g + 5])),
+                                         fmaxf(__uint_as_float(sv[8 * g + 6]), __uint_as_float(sv[8 * g + 7]))));
+          rs4[g & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+          ptx::st_shared_v4(pr + ((uint32_t(g) ^ sw) << 4), ptx::pack_bf16x2(e[0], e[1]), ptx::pack_bf16x2(e[2], e[3]),
+                            ptx::pack_bf16x2(e[4], e[5]), ptx::pack_bf16x2(e[6], e[7]));
+        }
       }
-      const float mt = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      // ---- stabiliser: first tile adopts its max; later tiles only when the max grew by more than 2^8
-      if (j == 0) {
-        m_used = (mt == -INFINITY) ? 0.f : mt;      // a fully hidden row (rows >= L, never stored) uses 0
-      } else {
-        const bool grow = (mt - m_used) * c > RESCALE_LOG2;
-        if (__any_sync(0xffffffffu, grow)) {          // warp-uniform: tcgen05.ld/st are warp-collective
-          const float m_next = grow ? mt : m_used;
-          const float alpha = ptx::ex2_approx((m_used - m_next) * c);   // 1 for rows that keep their max
-          // PV_{j-1} has landed in O.  p_free[b] is waited at every use of buffer b, so this thread is never
-          // more than one phase behind it (an mbarrier parity wait cannot tell phase k from phase k+2; a
-          // barrier that is only waited on occasionally - the old o_full - silently aliases).
+      rowsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      rowmax = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    };
+
+    const bool tr = TRACE_ON && tracing && warp == 0 && lane == 0;
+#define TRS(slot) do { if (TRACE_ON && tr) trace[(slot) * 16 + j] = clock64(); } while (0)
+    ptx::mbar_wait(&bars->s_full[0], 0);
+    ptx::tc_fence_after();
+    load_scores(0);
+    ptx::tmem_ld_wait();
+
+    for (int j = 0; j < n_kv; ++j) {
+      TRS(0);
+      const int n_groups = tile_keys_of(j) > 32 ? 8 : 4;   // 8-key groups holding visible keys (warp-uniform)
+      uint8_t* pr = p_row + (j & 1) * P_BYTES;
+      // P buffer j & 1 was last read by PV_{j-2}.  The tensor pipe retires one thread's MMAs in issue order and
+      // S_j was issued after PV_{j-2}, so having seen s_full for S_j implies that buffer is free: no wait here.
+      mask_scores(j);
+      if (j == 0) {   // first tile: adopt its true row max (a fully hidden row - rows >= L, never stored - uses 0)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 64; i += 2)
+          if (i < 8 * n_groups)
+            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+        const float mt0 = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        m_used = (mt0 == -INFINITY) ? 0.f : mt0;
+      }
+      TRS(1);
+      float rs, mt;
+      exp_pass(pr, m_used * c, n_groups, rs, mt);
+      TRS(2);
+      // ---- stale stabiliser check: only when some row's max grew by more than 2^RESCALE is O touched
+      const bool grow = (mt - m_used) * c > RESCALE_LOG2;
+      if (__any_sync(0xffffffffu, grow)) {          // warp-uniform: tcgen05.ld/st are warp-collective
+        const float m_next = grow ? mt : m_used;
+        const float alpha = ptx::ex2_approx((m_used - m_next) * c);   // 1 for rows that keep their max
+        if (j > 0) {
+          // PV_{j-1} must have landed in O.  p_free[b] phase k completes with PV_{b+2k}; S_j complete implies
+          // PV_{j-3} complete (issue order), so the barrier is in phase (j-1)>>1 or one past it: the parity
+          // wait is unambiguous.
           ptx::mbar_wait(&bars->p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll
@@ -258,53 +296,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ptx::tmem_st_32x32b_x32(t_o + hh * 32, v);
           }
           ptx::tmem_st_wait();
-          l *= alpha;
-          m_used = m_next;
         }
+        l *= alpha;
+        m_used = m_next;
+        // redo the tile against the new stabiliser (S_j is still in TMEM: it is released by the p_full arrive)
+        load_scores(j);
+        ptx::tmem_ld_wait();
+        mask_scores(j);
+        exp_pass(pr, m_used * c, n_groups, rs, mt);
       }
-      const float mc = m_used * c;
-      // ---- p = exp2((s - m) * c) as packed bf16 pairs, fp32 row sum (4 chains)
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[32];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(sv[i]), c, -mc));
-        const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
-        rs4[(i >> 1) & 3] += e0 + e1;
-        pk[i >> 1] = ptx::pack_bf16x2(e0, e1);
-      }
-      if (two_halves) {
-#pragma unroll
-        for (int i = 32; i < 64; i += 2) {
-          const float e0 = ptx::ex2_approx(fmaf(__uint_as_float(sv[i]), c, -mc));
-          const float e1 = ptx::ex2_approx(fmaf(__uint_as_float(sv[i + 1]), c, -mc));
-          rs4[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = ptx::pack_bf16x2(e0, e1);
-        }
-      }
-      l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      l += rs;
       TRS(3);
-      // ---- P_j -> smem buffer j & 1 once its previous reader PV_{j-2} is done (two tiles ago: no stall).
-      //      p_free[b] completes once per use of buffer b, so use number (j >> 1) - 1 is always the current
-      //      or the immediately preceding phase (mbarrier parity waits cannot look further back).
-      if (j > 1) ptx::mbar_wait(&bars->p_free[j & 1], ((j >> 1) - 1) & 1);
-      TRS(4);
-      uint8_t* pr = p_row + (j & 1) * P_BYTES;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)
-        ptx::st_shared_v4(pr + ((uint32_t(q4) ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2],
-                          pk[4 * q4 + 3]);
-      if (two_halves) {
-#pragma unroll
-        for (int q4 = 4; q4 < 8; ++q4)
-          ptx::st_shared_v4(pr + ((uint32_t(q4) ^ sw) << 4), pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2],
-                            pk[4 * q4 + 3]);
+      // ---- prefetch S_{j+1} into registers while the P hand-over is in flight
+      if (j + 1 < n_kv) {
+        ptx::mbar_wait(&bars->s_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        load_scores(j + 1);
       }
-      TRS(5);
+      TRS(4);
       ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars->p_full[j & 1]);
+      if (lane == 0) ptx::mbar_arrive(&bars->p_full[j & 1]);   // P_j in smem, S[j & 1] drained, O rescaled if needed
+      TRS(5);
+      ptx::tmem_ld_wait();
       TRS(6);
     }
     // ---- O is complete once the last PV has landed: normalise by the row sum and store
@@ -340,6 +355,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace attn
 
+constexpr int ATTN_POLY_DEFAULT = 0;
 namespace {
 long long* g_trace = nullptr;   // diagnostics only (aaclip_attention_trace)
 int g_trace_cta = -1;
@@ -354,19 +370,30 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   if (rc) return rc;
   rc = host::make_tmap_2d(&tmKV, qkv, (uint64_t)B * L, 3 * W, 3 * W, attn::BKV);
   if (rc) return rc;
-  static bool configured = false;
-  static int smem_bytes = attn::SMEM_BYTES;
-  if (!configured) {
-    // diagnostics: AACLIP_ATTN_PAD_SMEM=<bytes> pads the dynamic smem request (forces 1 CTA/SM for experiments)
-    if (getenv("AACLIP_ATTN_PAD_SMEM")) smem_bytes += atoi(getenv("AACLIP_ATTN_PAD_SMEM"));
-    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-    configured = true;
+  // AACLIP_ATTN_POLY=<0..4> (diagnostics): exponentials per 8 evaluated on the FMA pipe instead of the SFU
+  static int poly = getenv("AACLIP_ATTN_POLY") ? atoi(getenv("AACLIP_ATTN_POLY")) : ATTN_POLY_DEFAULT;
+  static float rescale = getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f;
+  typedef void (*Kern)(const CUtensorMap, const CUtensorMap, __nv_bfloat16*, int, int, int, long long*, int, float);
+  Kern kern = nullptr;
+  if (g_trace) kern = attn::attention_kernel<true, 0>;
+  else switch (poly) {
+    case 0: kern = attn::attention_kernel<false, 0>; break;
+    case 1: kern = attn::attention_kernel<false, 1>; break;
+    case 2: kern = attn::attention_kernel<false, 2>; break;
+    case 3: kern = attn::attention_kernel<false, 3>; break;
+    case 4: kern = attn::attention_kernel<false, 4>; break;
+    default: return host::fail(host::ERR_INVALID, "AACLIP_ATTN_POLY=%d out of range [0,4]", poly);
+  }
+  static Kern configured[8] = {nullptr};
+  bool seen = false;
+  for (Kern kk : configured) seen = seen || (kk == kern);
+  if (!seen) {
+    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    for (Kern& kk : configured) if (!kk) { kk = kern; break; }
   }
   dim3 grid((L + attn::BQ - 1) / attn::BQ, heads, B);
-  attn::attention_kernel<<<grid, attn::THREADS, smem_bytes, stream>>>(
-      tmQ, tmKV, static_cast<__nv_bfloat16*>(out), L, heads, causal, g_trace, g_trace_cta,
-      getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f);
+  kern<<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(tmQ, tmKV, static_cast<__nv_bfloat16*>(out), L, heads, causal,
+                                                          g_trace, g_trace_cta, rescale);
   AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }

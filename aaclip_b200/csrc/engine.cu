@@ -101,6 +101,7 @@ struct ProfRec { int cls; cudaEvent_t a, b; };
 
 struct aaclip_ctx {
   bool prof_on = false;
+  double prof_span_ms = 0.0;   // first launch start -> last launch end of the log read last
   std::vector<ProfRec> prof;
   aaclip_cfg cfg;
   int device = 0;
@@ -363,6 +364,11 @@ extern "C" int aaclip_profile_read(aaclip_ctx* c, double* ms, long long* counts,
   AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
   AACLIP_CUDA_CHECK(cudaDeviceSynchronize());
   for (int i = 0; i < n_classes; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  c->prof_span_ms = 0.0;
+  if (!c->prof.empty()) {
+    float span = 0.f;
+    if (cudaEventElapsedTime(&span, c->prof.front().a, c->prof.back().b) == cudaSuccess) c->prof_span_ms = span;
+  }
   for (auto& r : c->prof) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.cls < n_classes) { ms[r.cls] += t; counts[r.cls]++; }
@@ -371,6 +377,8 @@ extern "C" int aaclip_profile_read(aaclip_ctx* c, double* ms, long long* counts,
   c->prof.clear();
   return host::OK;
 }
+
+extern "C" double aaclip_profile_span_ms(const aaclip_ctx* c) { return c ? c->prof_span_ms : 0.0; }
 
 extern "C" long long aaclip_device_bytes(const aaclip_ctx* c) { return c ? c->bytes : 0; }
 extern "C" long long aaclip_launch_count(const aaclip_ctx* c) { return c ? c->launches : 0; }

@@ -262,6 +262,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N, int a_m
 __device__ __forceinline__ float ex2_approx(float x) {
   float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
+// 2^x on the FMA / ALU pipes (no SFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f
+// (relative error 1.0e-4, far below the bf16 rounding of the probabilities it feeds), exponent patched in with an
+// integer add.  x is clamped at -126, so -inf (masked keys) gives 2^-126 ~ 0.  Valid for x < 127.
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xr = x + 12582912.0f;          // 1.5 * 2^23: rounds x to the nearest integer in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);
+  float p = fmaf(f, 0.05500893f, 0.24221096f);
+  p = fmaf(p, f, 0.69328293f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }

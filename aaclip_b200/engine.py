@@ -141,6 +141,7 @@ class Engine:
         ms = (C.c_double * n)()
         cnt = (C.c_longlong * n)()
         check(self.lib.aaclip_profile_read(self._ctx, ms, cnt, n))
+        self.profile_span_ms = float(self.lib.aaclip_profile_span_ms(self._ctx))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(_lib.PROFILE_CLASSES)}
 
     # ------------------------------------------------------------------ forward

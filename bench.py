@@ -114,7 +114,7 @@ def cpu_port_images_per_s(n_images: int, threads: int):
     return n_images / dt, dt
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,13 +156,23 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    chatter) goes to stderr.  Returns a file object bound to the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
     args = parse()
+    out = _claim_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as dist
@@ -241,6 +251,7 @@ def main():
     eng.profile(False)
     kern = {}
     tot_ms = sum(v[0] for v in prof.values()) / prof_steps
+    span_ms = eng.profile_span_ms / prof_steps   # profiled step incl. the idle time between kernels
     for name, (pms, cnt) in prof.items():
         if cnt:
             kern[name] = {"ms_per_step": pms / prof_steps, "launches_per_step": cnt // prof_steps,
@@ -334,11 +345,13 @@ def main():
                        "l2": f"inputs rotate over {n_rot} batches ({n_rot * B * 3 * cfg.image_size ** 2 * 4 / 1e6:.0f} MB > 126 MB L2); "
                              "per-step activation traffic (>1.3 GB) exceeds L2",
                        "outputs_finite": finite},
-            "roofline": roofline, "roofline_head": head, "kernels": kern, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "roofline_head": head, "kernels": kern,
+            "profiled_step": {"span_ms": span_ms, "sum_kernel_ms": tot_ms, "idle_between_kernels_ms": span_ms - tot_ms,
+                              "note": "2 extra steps with CUDA events around every launch"}, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

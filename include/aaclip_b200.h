@@ -133,6 +133,9 @@ long long aaclip_launch_count(const aaclip_ctx* ctx);
 #define AACLIP_PROFILE_CLASSES 16
 int aaclip_profile_enable(aaclip_ctx* ctx, int on);
 int aaclip_profile_read(aaclip_ctx* ctx, double* ms, long long* counts, int n_classes);
+/* Milliseconds from the start of the first to the end of the last launch of the log aaclip_profile_read consumed
+ * last (span - sum of durations = idle time between kernels). */
+double aaclip_profile_span_ms(const aaclip_ctx* ctx);
 
 /* ---- AdaptedCLIP.forward (model/adapter.py:67-112) ------------------------------------------------- */
 /* image fp32 [B,3,S,S] (CLIP-normalised).  seg_out[i]: fp32 [B,P,E] L2-normalised patch tokens of level i

@@ -6,5 +6,6 @@ print(f"gemm: {r['achieved']:.0f} TF/s frac={r['frac']:.3f} (burst {r['frac_of_b
 print("head:", d.get("roofline_head"))
 for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["ms_per_step"]):
     print(f"  {k:14s} {v['ms_per_step']:8.3f} ms  x{v['launches_per_step']:3d}  share {v['share']:.3f}" + (f"  {v['tflops']:.0f} TF/s" if 'tflops' in v else ""))
+if d.get("profiled_step"): print("profiled step:", d["profiled_step"])
 print("sum kernels ms:", sum(v["ms_per_step"] for v in d["kernels"].values()))
 if d.get("cpu_baseline"): print("cpu:", d["cpu_baseline"])
