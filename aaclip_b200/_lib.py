@@ -61,6 +61,8 @@ SIGNATURES = {
     "aaclip_anomaly_head": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "aaclip_forward_fused": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "aaclip_forward_fused_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "aaclip_submit_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, C.POINTER(_ll)]),
+    "aaclip_wait_host": (_i, [_vp, _ll]),
     "aaclip_text_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "aaclip_text_anchor": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "aaclip_gemm_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),

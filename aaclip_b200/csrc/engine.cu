@@ -124,9 +124,17 @@ struct aaclip_ctx {
   int cap_rows = 0;  // rows of the token-major buffers
   float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr;
   bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *col = nullptr, *tap = nullptr;
-  float *dev_anchors = nullptr, *dev_maps = nullptr, *dev_scores = nullptr, *dev_image = nullptr;  // *_host entry
+  // host-buffer pipeline (aaclip_submit_host / aaclip_wait_host): two slots of device staging, copy-in, compute
+  // and copy-out streams, so the H2D of batch k+1 and the D2H of batch k-1 overlap the compute of batch k
+  struct HostSlot {
+    float *img = nullptr, *maps = nullptr, *scores = nullptr, *anchors = nullptr;
+    cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    bool busy = false;
+    long long ticket = -1;
+  } slots[2];
+  long long next_ticket = 0;
   long long stage_cap = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
 
   template <typename T>
   int alloc(T** p, long long n) {
@@ -347,7 +355,14 @@ extern "C" void aaclip_destroy(aaclip_ctx* c) {
   cudaDeviceSynchronize();
   for (void* p : c->allocs) cudaFree(p);
   if (c->stage) cudaFree(c->stage);
+  for (auto& sl : c->slots) {
+    if (sl.in_done) cudaEventDestroy(sl.in_done);
+    if (sl.comp_done) cudaEventDestroy(sl.comp_done);
+    if (sl.out_done) cudaEventDestroy(sl.out_done);
+  }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->in_stream) cudaStreamDestroy(c->in_stream);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
   delete c;
 }
 
@@ -509,34 +524,93 @@ extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, co
   return host::OK;
 }
 
+namespace {
+int ensure_host_pipeline(aaclip_ctx* c) {
+  if (c->in_stream) return host::OK;
+  const int S = c->cfg.image_size, mb = c->cfg.max_batch;
+  AACLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  AACLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+  AACLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+  for (auto& sl : c->slots) {
+    TRY(c->alloc(&sl.img, 3LL * mb * S * S)); TRY(c->alloc(&sl.maps, (long long)mb * S * S));
+    TRY(c->alloc(&sl.scores, mb)); TRY(c->alloc(&sl.anchors, 2LL * c->E));
+    AACLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+    AACLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sl.comp_done, cudaEventDisableTiming));
+    AACLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+  }
+  return host::OK;
+}
+}  // namespace
+
+extern "C" int aaclip_submit_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors, int mode,
+                                  float* host_maps_out, float* host_scores_out, long long* ticket) {
+  TRY(check_ready(c));
+  if (!host_image || !host_anchors || !ticket) return host::fail(host::ERR_INVALID, "submit_host: null argument");
+  if (B < 1 || B > c->cfg.max_batch)
+    return host::fail(host::ERR_INVALID, "submit_host: B=%d outside [1, max_batch=%d]", B, c->cfg.max_batch);
+  if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
+    return host::fail(host::ERR_INVALID, "submit_host: only the test modes are fused (mode=%d)", mode);
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  TRY(ensure_host_pipeline(c));
+  aaclip_ctx::HostSlot& sl = c->slots[c->next_ticket & 1];
+  if (sl.busy)
+    return host::fail(host::ERR_STATE, "submit_host: ticket %lld is still in flight (at most 2 batches may be pending)",
+                      sl.ticket);
+  const int S = c->cfg.image_size;
+  // copy-in: the slot's previous batch was waited for on the host, so its staging buffers are free
+  AACLIP_CUDA_CHECK(cudaMemcpyAsync(sl.anchors, host_anchors, 2LL * c->E * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+  AACLIP_CUDA_CHECK(cudaMemcpyAsync(sl.img, host_image, 3LL * B * S * S * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+  AACLIP_CUDA_CHECK(cudaEventRecord(sl.in_done, c->in_stream));
+  // compute (serial over batches on one stream: the workspaces are shared)
+  AACLIP_CUDA_CHECK(cudaStreamWaitEvent(c->own_stream, sl.in_done, 0));
+  TRY(aaclip_forward_fused(c, sl.img, B, sl.anchors, mode, host_maps_out ? sl.maps : nullptr,
+                           host_scores_out ? sl.scores : nullptr, c->own_stream));
+  AACLIP_CUDA_CHECK(cudaEventRecord(sl.comp_done, c->own_stream));
+  // copy-out
+  AACLIP_CUDA_CHECK(cudaStreamWaitEvent(c->out_stream, sl.comp_done, 0));
+  if (host_maps_out)
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_maps_out, sl.maps, (long long)B * S * S * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+  if (host_scores_out)
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_scores_out, sl.scores, B * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+  AACLIP_CUDA_CHECK(cudaEventRecord(sl.out_done, c->out_stream));
+  sl.busy = true;
+  sl.ticket = c->next_ticket;
+  *ticket = c->next_ticket++;
+  return host::OK;
+}
+
+extern "C" int aaclip_wait_host(aaclip_ctx* c, long long ticket) {
+  TRY(check_ready(c));
+  aaclip_ctx::HostSlot& sl = c->slots[ticket & 1];
+  if (ticket < 0 || sl.ticket != ticket || !sl.busy)
+    return host::fail(host::ERR_STATE, "wait_host: ticket %lld is not pending", ticket);
+  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  AACLIP_CUDA_CHECK(cudaEventSynchronize(sl.out_done));
+  sl.busy = false;
+  return host::OK;
+}
+
 extern "C" int aaclip_forward_fused_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors,
                                          int mode, float* host_maps_out, float* host_scores_out) {
   TRY(check_ready(c));
   if (B <= 0) return host::OK;
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
-  if (!c->own_stream) AACLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  cudaStream_t st = c->own_stream;
+  for (const auto& sl : c->slots)
+    if (sl.busy) return host::fail(host::ERR_STATE, "forward_fused_host: ticket %lld is still pending", sl.ticket);
   const int S = c->cfg.image_size, mb = c->cfg.max_batch;
   const long long img_elems = 3LL * S * S;
-  if (!c->dev_image) {
-    TRY(c->alloc(&c->dev_image, mb * img_elems)); TRY(c->alloc(&c->dev_maps, (long long)mb * S * S));
-    TRY(c->alloc(&c->dev_scores, mb)); TRY(c->alloc(&c->dev_anchors, 2LL * c->E));
-  }
-  AACLIP_CUDA_CHECK(cudaMemcpyAsync(c->dev_anchors, host_anchors, 2LL * c->E * sizeof(float), cudaMemcpyHostToDevice, st));
+  // chunks of max_batch images run through the two-slot pipeline: chunk k+1 uploads while chunk k computes
+  long long pending[2] = {-1, -1};
+  int n_pending = 0;
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int nb = std::min(mb, B - b0);
-    AACLIP_CUDA_CHECK(cudaMemcpyAsync(c->dev_image, host_image + b0 * img_elems, nb * img_elems * sizeof(float),
-                                      cudaMemcpyHostToDevice, st));
-    TRY(aaclip_forward_fused(c, c->dev_image, nb, c->dev_anchors, mode, host_maps_out ? c->dev_maps : nullptr,
-                             host_scores_out ? c->dev_scores : nullptr, st));
-    if (host_maps_out)
-      AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_maps_out + (long long)b0 * S * S, c->dev_maps,
-                                        (long long)nb * S * S * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (host_scores_out)
-      AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_scores_out + b0, c->dev_scores, nb * sizeof(float),
-                                        cudaMemcpyDeviceToHost, st));
+    if (n_pending == 2) { TRY(aaclip_wait_host(c, pending[0])); pending[0] = pending[1]; n_pending = 1; }
+    long long t = -1;
+    TRY(aaclip_submit_host(c, host_image + b0 * img_elems, nb, host_anchors, mode,
+                           host_maps_out ? host_maps_out + (long long)b0 * S * S : nullptr,
+                           host_scores_out ? host_scores_out + b0 : nullptr, &t));
+    pending[n_pending++] = t;
   }
-  AACLIP_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int i = 0; i < n_pending; ++i) TRY(aaclip_wait_host(c, pending[i]));
   return host::OK;
 }
 

@@ -187,6 +187,46 @@ class Engine:
         check(self.lib.aaclip_forward_fused_host(self._ctx, image.data_ptr(), image.shape[0], anchors.data_ptr(),
                                                  DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr()))
 
+    def submit_host(self, image: torch.Tensor, anchors: torch.Tensor, maps_out: torch.Tensor,
+                    scores_out: torch.Tensor, domain: str = "Industrial") -> int:
+        """Asynchronous host-buffer entry: enqueues H2D -> forward -> D2H for one batch (<= max_batch images) and
+        returns a ticket; at most two tickets may be pending.  The CPU tensors must stay alive until wait_host."""
+        for t in (image, anchors, maps_out, scores_out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("submit_host takes contiguous float32 CPU tensors")
+        ticket = C.c_longlong(-1)
+        check(self.lib.aaclip_submit_host(self._ctx, image.data_ptr(), image.shape[0], anchors.data_ptr(),
+                                          DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr(),
+                                          C.byref(ticket)))
+        return int(ticket.value)
+
+    def wait_host(self, ticket: int) -> None:
+        check(self.lib.aaclip_wait_host(self._ctx, ticket))
+
+    def predict_stream(self, batches, anchors: torch.Tensor, domain: str = "Industrial"):
+        """The loop of test.py:get_predictions (test.py:53-99) over an iterable of CPU image batches, pipelined:
+        while batch k computes, batch k+1 uploads and batch k-1 downloads.  Yields (maps [B,S,S], scores [B]) as
+        pinned CPU tensors, in order."""
+        S = self.cfg.image_size
+        anchors = anchors.detach().float().cpu().contiguous()
+        pending = []
+        for img in batches:
+            img = img.detach()
+            if img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous():
+                img = img.float().cpu().contiguous()
+            if not img.is_pinned():
+                img = img.pin_memory()
+            maps = torch.empty(img.shape[0], S, S).pin_memory()
+            scores = torch.empty(img.shape[0]).pin_memory()
+            if len(pending) == 2:
+                t, keep = pending.pop(0)
+                self.wait_host(t)
+                yield keep[1], keep[2]
+            pending.append((self.submit_host(img, anchors, maps, scores, domain), (img, maps, scores)))
+        for t, keep in pending:
+            self.wait_host(t)
+            yield keep[1], keep[2]
+
     def text_forward(self, tokens: torch.Tensor) -> torch.Tensor:
         """AdaptedCLIP.encode_text(adapt_text=True): int32 [n, ctx] -> fp32 [n, t_width]."""
         if not self.has_text:

@@ -156,9 +156,19 @@ int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg_is_bf16, c
 /* ---- fused image -> anomaly map (AdaptedCLIP.forward + head, no seg-token materialisation) ---------- */
 int aaclip_forward_fused(aaclip_ctx* ctx, const float* image, int B, const float* anchors /*[E,2]*/, int mode,
                          float* maps_out /*[B,S,S]*/, float* scores_out /*[B]*/, void* stream);
-/* Same with HOST buffers (pinned or pageable): H2D of the images, D2H of maps and scores, synchronous. */
+/* Same with HOST buffers (pinned or pageable): H2D of the images, D2H of maps and scores, synchronous.
+ * B > max_batch is processed in chunks through the two-slot pipeline below. */
 int aaclip_forward_fused_host(aaclip_ctx* ctx, const float* host_image, int B, const float* host_anchors, int mode,
                               float* host_maps_out, float* host_scores_out);
+
+/* Pipelined form of the host-buffer entry, for a loop over batches (test.py:get_predictions, test.py:53-99):
+ * submit enqueues H2D (copy-in stream) -> forward (compute stream) -> D2H (copy-out stream) for one batch of
+ * B <= max_batch images and returns a ticket at once; wait blocks until that batch's maps and scores have landed in
+ * the host buffers.  Two batches may be in flight, so the copies of neighbouring batches overlap the compute.
+ * Host buffers must stay valid (and should be pinned) until the ticket has been waited for. */
+int aaclip_submit_host(aaclip_ctx* ctx, const float* host_image, int B, const float* host_anchors, int mode,
+                       float* host_maps_out, float* host_scores_out, long long* ticket);
+int aaclip_wait_host(aaclip_ctx* ctx, long long ticket);
 
 /* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
 /* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */

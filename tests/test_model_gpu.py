@@ -123,6 +123,42 @@ def test_host_buffer_entry(full):
     assert torch.equal(maps, m_dev.cpu()) and torch.equal(scores, s_dev.cpu())
 
 
+def test_host_pipeline_matches_device_entry(full):
+    """submit_host / wait_host (two batches in flight), chunked forward_fused_host (B > max_batch) and
+    predict_stream give bit-identical results to the device-pointer entry, in order."""
+    from aaclip_b200 import synth
+    cfg, eng, *_ = full
+    T = synth.anchors(cfg, seed=1)
+    batches = [synth.images(n, cfg, seed=40 + i) for i, n in enumerate((4, 1, 3, 4, 2))]
+    ref = []
+    for b in batches:
+        m, s = eng.forward_fused(b.cuda(), T.cuda())
+        ref.append((m.cpu(), s.cpu()))
+    got = list(eng.predict_stream(batches, T))
+    assert len(got) == len(ref)
+    for (m, s), (mr, sr) in zip(got, ref):
+        assert torch.equal(m, mr) and torch.equal(s, sr)
+    # a third submit without a wait is refused (two slots), then the pipeline drains normally
+    bufs = [(b.pin_memory(), torch.empty(b.shape[0], 336, 336).pin_memory(), torch.empty(b.shape[0]).pin_memory())
+            for b in batches[:3]]
+    t0 = eng.submit_host(bufs[0][0], T, bufs[0][1], bufs[0][2])
+    t1 = eng.submit_host(bufs[1][0], T, bufs[1][1], bufs[1][2])
+    with pytest.raises(RuntimeError):
+        eng.submit_host(bufs[2][0], T, bufs[2][1], bufs[2][2])
+    eng.wait_host(t0)
+    t2 = eng.submit_host(bufs[2][0], T, bufs[2][1], bufs[2][2])
+    eng.wait_host(t1); eng.wait_host(t2)
+    with pytest.raises(RuntimeError):
+        eng.wait_host(t2)
+    for (_, m, s), (mr, sr) in zip(bufs, ref):
+        assert torch.equal(m, mr) and torch.equal(s, sr)
+    # B = 6 > max_batch = 4 through the synchronous entry: chunks of 4 + 2 ride the same two slots
+    big = torch.cat([batches[0], batches[4]]).pin_memory()
+    maps, scores = torch.empty(6, 336, 336).pin_memory(), torch.empty(6).pin_memory()
+    eng.forward_fused_host(big, T, maps, scores)
+    assert torch.equal(maps, torch.cat([ref[0][0], ref[4][0]])) and torch.equal(scores, torch.cat([ref[0][1], ref[4][1]]))
+
+
 def test_text_path_vs_golden(full):
     import aaclip_oracle as orc
     from aaclip_b200 import synth
