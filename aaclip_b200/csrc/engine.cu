@@ -122,7 +122,7 @@ struct aaclip_ctx {
   bf16* t_final = nullptr;
   // workspaces
   int cap_rows = 0;  // rows of the token-major buffers
-  float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr;
+  float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr, *rownorm = nullptr;
   bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *col = nullptr, *tap = nullptr;
   // host-buffer pipeline (aaclip_submit_host / aaclip_wait_host): two slots of device staging, copy-in, compute
   // and copy-out streams, so the H2D of batch k+1 and the D2H of batch k-1 overlap the compute of batch k
@@ -258,7 +258,7 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
       if (so || dl) {
         RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
       }
-      if (want_det) RUN(PC_DET_MEAN, k::launch_det_mean(c->s, 2 * E, E, B, P, E, det_out, st));
+      if (want_det) { RUN(PC_DET_MEAN, k::launch_det_mean(c->s, 2 * E, E, B, P, E, c->rownorm, det_out, st)); c->launches++; }
       ++level;
     }
   }
@@ -343,7 +343,7 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
   A(c->alloc(&c->x, rows * max_w)); A(c->alloc(&c->a, rows * max_w)); A(c->alloc(&c->xn, rows * max_w));
   A(c->alloc(&c->qkv, rows * 3 * max_w)); A(c->alloc(&c->att, rows * max_w)); A(c->alloc(&c->h, rows * max_ff));
   A(c->alloc(&c->col, prow * c->Kpad)); A(c->alloc(&c->tap, prow * w)); A(c->alloc(&c->s, prow * 2 * E));
-  A(c->alloc(&c->dots, (long long)cfg->n_levels * prow * 2)); A(c->alloc(&c->det, (long long)cfg->max_batch * E));
+  A(c->alloc(&c->dots, (long long)cfg->n_levels * prow * 2)); A(c->alloc(&c->det, (long long)cfg->max_batch * E)); A(c->alloc(&c->rownorm, prow));
   if (rc != host::OK) { aaclip_destroy(c); return rc; }
   *out = c;
   return host::OK;

@@ -3,9 +3,9 @@
 //
 //   patch_dots_kernel : one warp per patch token; 16-byte coalesced loads of the (bf16 or fp32) normalised
 //                       tokens of every level, warp-shuffle dot products with both text anchors.
-//   head_maps_kernel  : per (image, band of output rows): builds A = U_bilinear . G_blur  (S x G, the blur
-//                       with reflect padding and the align_corners=True upsample are both separable and
-//                       linear, so map = A . m . A^T), then writes the fp32 map with coalesced stores.
+//   head_maps_kernel  : per (image, band of output rows): level-summed patch map in smem, separable gaussian
+//                       blur with reflect padding on the G x G grid, then the align_corners=True bilinear
+//                       upsample as 4 taps per output pixel, float4 coalesced stores of the fp32 map.
 //                       Train mode (test=False): no blur, both channels, softmax over channels, per level.
 //
 // Test mode, summed over levels (test.py:93):   m[h][w] = sum_l (100*(d1-d0) + 1)/2 = 50*sum_l(d1-d0) + n_levels/2
@@ -76,13 +76,19 @@ constexpr int HEAD_THREADS = 256;
 // mode: AACLIP_HEAD_*.  dots: [n_levels][B*G*G][2].
 // test modes : maps [B][S][S]; level-summed.  grid = (bands, B, 1)
 // train mode : maps [n_levels][B][2][S][S]; softmax over the 2 channels. grid = (bands, B, n_levels)
+//
+// The blur (reflect padding) and the align_corners=True bilinear upsample are applied in the reference's order
+// on the G x G patch map: blur rows, blur columns (kornia's separable filter), then each output pixel is the
+// 4-tap bilinear blend of the blurred map, float4 stores along x.  Every block redoes the tiny blur of the whole
+// G x G map (2 * G*G*ksize FMAs) rather than share it through global memory.
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int S, int mode,
                  float* __restrict__ maps) {
   extern __shared__ float sm[];
-  float* A = sm;                    // [S][G]
-  float* m = A + (size_t)S * G;     // [C][G][G]
-  float* t = m + 2 * G * G;         // [G][HEAD_THREADS]
+  const int P = G * G;
+  float* m = sm;                 // [C][G][G]  per-patch scalars
+  float* t = m + 2 * P;          // [C][G][G]  after the row blur
+  float* mb = t + 2 * P;         // [C][G][G]  blurred map
   __shared__ float wk[16];
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -90,8 +96,8 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
   const bool train = (mode == AACLIP_HEAD_TRAIN_SOFTMAX);
   const int ksize = train ? 1 : (mode == AACLIP_HEAD_TEST_INDUSTRIAL ? 7 : 9);
   const float sigma = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 1.0f : 1.5f;
-  const int P = G * G;
   const size_t rows = (size_t)B * P;
+  const int C = train ? 2 : 1;
 
   // 1-D gaussian taps, normalised to sum 1 (kornia 0.6.9 gaussian(); odd window)
   if (tid == 0) {
@@ -120,58 +126,73 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
     }
   }
   __syncthreads();
-  // A[x][g] = l0 * Gm[r0][g] + l1 * Gm[r1][g],  Gm = blur matrix with reflect padding (identity in train mode)
-  const float scale = (S > 1) ? float(G - 1) / float(S - 1) : 0.f;
-  for (int i = tid; i < S * G; i += HEAD_THREADS) {
-    const int x = i / G, g = i - x * G;
-    const float src = scale * float(x);
-    int r0 = int(src);
-    if (r0 > G - 1) r0 = G - 1;
-    const int r1 = r0 + ((r0 < G - 1) ? 1 : 0);
-    const float l1 = src - float(r0), l0 = 1.0f - l1;
-    float g0 = 0.f, g1 = 0.f;
-    for (int tt = 0; tt < ksize; ++tt) {
-      const int off = tt - ksize / 2;
-      if (reflect_idx(r0 + off, G) == g) g0 += wk[tt];
-      if (reflect_idx(r1 + off, G) == g) g1 += wk[tt];
+  const float* src_map = m;
+  if (!train) {
+    // blur along x, then along y (reflect padding: forward_utils.py:208-210)
+    const int half = ksize / 2;
+    for (int i = tid; i < P; i += HEAD_THREADS) {
+      const int gy = i / G, gx = i - gy * G;
+      float acc = 0.f;
+      for (int tt = 0; tt < ksize; ++tt) acc += wk[tt] * m[gy * G + reflect_idx(gx + tt - half, G)];
+      t[i] = acc;
     }
-    A[i] = l0 * g0 + l1 * g1;
+    __syncthreads();
+    for (int i = tid; i < P; i += HEAD_THREADS) {
+      const int gy = i / G, gx = i - gy * G;
+      float acc = 0.f;
+      for (int tt = 0; tt < ksize; ++tt) acc += wk[tt] * t[reflect_idx(gy + tt - half, G) * G + gx];
+      mb[i] = acc;
+    }
+    __syncthreads();
+    src_map = mb;
   }
-  __syncthreads();
 
+  // bilinear, align_corners=True: src = dst * (G-1)/(S-1)   (forward_utils.py:211-213)
+  const float scale = (S > 1) ? float(G - 1) / float(S - 1) : 0.f;
   const int y0 = blockIdx.x * BAND;
   const int ny = min(BAND, S - y0);
-  const int C = train ? 2 : 1;
-  for (int x = tid; x < S; x += HEAD_THREADS) {
-    float o0[BAND];
-    const float* Ax = A + (size_t)x * G;
-    for (int c = 0; c < C; ++c) {
-      // t[g1] = sum_g2 m_c[g1][g2] * A[x][g2]
-      for (int g1 = 0; g1 < G; ++g1) {
-        float acc = 0.f;
-        const float* mr = m + c * P + g1 * G;
-        for (int g2 = 0; g2 < G; ++g2) acc += mr[g2] * Ax[g2];
-        t[g1 * HEAD_THREADS + tid] = acc;
-      }
+  const int xq = (S + 3) / 4;               // float4 groups per row
+  for (int i = tid; i < ny * xq; i += HEAD_THREADS) {
+    const int yy = i / xq, x4 = (i - yy * xq) * 4;
+    const int y = y0 + yy;
+    const float sy = scale * float(y);
+    int ry0 = min(int(sy), G - 1);
+    const int ry1 = ry0 + ((ry0 < G - 1) ? 1 : 0);
+    const float ly1 = sy - float(ry0), ly0 = 1.0f - ly1;
+    float o[2][4];
 #pragma unroll
-      for (int yy = 0; yy < BAND; ++yy) {
-        if (yy < ny) {
-          const float* Ay = A + (size_t)(y0 + yy) * G;
-          float acc = 0.f;
-          for (int g1 = 0; g1 < G; ++g1) acc += Ay[g1] * t[g1 * HEAD_THREADS + tid];
-          if (!train) {
-            maps[((size_t)b * S + (y0 + yy)) * S + x] = acc;
-          } else if (c == 0) {
-            o0[yy] = acc;
-          } else {
-            const float mx = fmaxf(o0[yy], acc);
-            const float e0 = expf(o0[yy] - mx), e1 = expf(acc - mx);
-            const float inv = 1.0f / (e0 + e1);
-            float* base = maps + (((size_t)lvl * B + b) * 2) * S * S + (size_t)(y0 + yy) * S + x;
-            base[0] = e0 * inv;
-            base[(size_t)S * S] = e1 * inv;
-          }
-        }
+    for (int e = 0; e < 4; ++e) {
+      const int x = min(x4 + e, S - 1);
+      const float sx = scale * float(x);
+      int rx0 = min(int(sx), G - 1);
+      const int rx1 = rx0 + ((rx0 < G - 1) ? 1 : 0);
+      const float lx1 = sx - float(rx0), lx0 = 1.0f - lx1;
+      for (int c = 0; c < C; ++c) {
+        const float* mc = src_map + c * P;
+        const float top = lx0 * mc[ry0 * G + rx0] + lx1 * mc[ry0 * G + rx1];
+        const float bot = lx0 * mc[ry1 * G + rx0] + lx1 * mc[ry1 * G + rx1];
+        o[c][e] = ly0 * top + ly1 * bot;
+      }
+    }
+    if (!train) {
+      float* dst = maps + ((size_t)b * S + y) * S + x4;
+      if (x4 + 3 < S && (S & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+      else for (int e = 0; e < 4 && x4 + e < S; ++e) dst[e] = o[0][e];
+    } else {
+      float p0[4], p1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float mx = fmaxf(o[0][e], o[1][e]);
+        const float e0 = expf(o[0][e] - mx), e1 = expf(o[1][e] - mx);
+        const float inv = 1.0f / (e0 + e1);
+        p0[e] = e0 * inv; p1[e] = e1 * inv;
+      }
+      float* base = maps + (((size_t)lvl * B + b) * 2) * S * S + (size_t)y * S + x4;
+      if (x4 + 3 < S && (S & 3) == 0) {
+        *reinterpret_cast<float4*>(base) = make_float4(p0[0], p0[1], p0[2], p0[3]);
+        *reinterpret_cast<float4*>(base + (size_t)S * S) = make_float4(p1[0], p1[1], p1[2], p1[3]);
+      } else {
+        for (int e = 0; e < 4 && x4 + e < S; ++e) { base[e] = p0[e]; base[(size_t)S * S + e] = p1[e]; }
       }
     }
   }
@@ -249,8 +270,8 @@ int k::launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_
   if (mode < 0 || mode > 2) return host::fail(host::ERR_INVALID, "head: mode %d", mode);
   const int pad = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 3 : (mode == AACLIP_HEAD_TEST_MEDICAL ? 4 : 0);
   if (G <= pad) return host::fail(host::ERR_INVALID, "head: grid %d too small for reflect padding %d", G, pad);
-  const size_t smem = ((size_t)S * G + 2 * G * G + (size_t)G * HEAD_THREADS) * sizeof(float);
-  if (smem > 227 * 1024) return host::fail(host::ERR_INVALID, "head: img_size %d / grid %d needs %zu B smem", S, G, smem);
+  const size_t smem = (size_t)6 * G * G * sizeof(float);
+  if (smem > 200 * 1024) return host::fail(host::ERR_INVALID, "head: img_size %d / grid %d needs %zu B smem", S, G, smem);
   static size_t configured = 0;
   if (smem > configured) {
     AACLIP_CUDA_CHECK(cudaFuncSetAttribute(head_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -33,7 +33,9 @@ int launch_l2norm_rows(const float* s, int ld, int col0, int rows, int width, fl
                        const float* anchors, float* dots, cudaStream_t stream);
 
 // det token: mean over P patches of the L2-normalised rows of s[b*P + p, col0:col0+width] -> det[b, width]
-int launch_det_mean(const float* s, int ld, int col0, int B, int P, int width, float* det, cudaStream_t stream);
+// (two launches; inv_scratch: B*P floats for the inverse row norms)
+int launch_det_mean(const float* s, int ld, int col0, int B, int P, int width, float* inv_scratch, float* det,
+                    cudaStream_t stream);
 
 // patch-embedding im2col: image fp32 [B,3,S,S] -> bf16 [B*G*G, Kpad], k = c*ps*ps + i*ps + j, zero padded
 int launch_im2col(const float* image, int B, int S, int ps, int Kpad, void* out_bf16, cudaStream_t stream);

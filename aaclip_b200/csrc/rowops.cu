@@ -156,30 +156,55 @@ l2norm_rows_kernel(const float* __restrict__ s, int ld, int col0, int rows, floa
   }
 }
 
-// det[b, :] = mean_p normalize(s[b*P + p, col0:col0+width])      (model/adapter.py:110-111)
-// one block per (image, 128-column slice): phase 1 row inverse norms into smem, phase 2 column means.
-__global__ void __launch_bounds__(256)
-det_mean_kernel(const float* __restrict__ s, int ld, int col0, int P, int width, float* __restrict__ det) {
-  extern __shared__ float inv_norm[];  // [P]
+// det[b, :] = mean_p normalize(s[b*P + p, col0:col0+width])      (model/adapter.py:110-111), two passes:
+//   row_inv_norm_kernel: one warp per row -> inv[r] = 1 / max(||row||, 1e-12)
+//   det_mean_kernel    : block per (image, 128-column slice); each warp sums P/8 rows (one float4 per lane), the 8
+//                        partial sums are combined through smem in a fixed order (deterministic, no atomics).
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+row_inv_norm_kernel(const float* __restrict__ s, int ld, int col0, int rows, int width, float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* row = s + (size_t)r * ld + col0;
+  float ss = 0.f;
+  for (int c = lane * 4; c < width; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  ss = ptx::warp_sum(ss);
+  if (lane == 0) inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+det_mean_kernel(const float* __restrict__ s, int ld, int col0, int P, int width, const float* __restrict__ inv,
+                float* __restrict__ det) {
+  __shared__ float4 part[WARPS_PER_BLOCK][32];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* base = s + (size_t)b * P * ld + col0;
-  for (int p = warp; p < P; p += 8) {
-    const float* row = base + (size_t)p * ld;
-    float ss = 0.f;
-    for (int c = lane * 4; c < width; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(row + c);
-      ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  const int c = blockIdx.y * 128 + lane * 4;
+  const bool live = c < width;
+  const float* base = s + (size_t)b * P * ld + col0 + c;
+  const float* iv = inv + (size_t)b * P;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+#pragma unroll 4
+    for (int p = warp; p < P; p += WARPS_PER_BLOCK) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * ld);
+      const float w = __ldg(iv + p);
+      acc.x += v.x * w; acc.y += v.y * w; acc.z += v.z * w; acc.w += v.w * w;
     }
-    ss = ptx::warp_sum(ss);
-    if (lane == 0) inv_norm[p] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
   }
+  part[warp][lane] = acc;
   __syncthreads();
-  const int c = blockIdx.y * 256 + threadIdx.x;
-  if (c < width) {
-    float acc = 0.f;
-    for (int p = 0; p < P; ++p) acc += base[(size_t)p * ld + c] * inv_norm[p];
-    det[(size_t)b * width + c] = acc / float(P);
+  if (warp == 0 && live) {
+    float4 t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < WARPS_PER_BLOCK; ++w) {
+      const float4 q = part[w][lane];
+      t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+    }
+    const float invP = 1.0f / float(P);
+    *reinterpret_cast<float4*>(det + (size_t)b * width + c) = make_float4(t.x * invP, t.y * invP, t.z * invP, t.w * invP);
   }
 }
 
@@ -273,11 +298,15 @@ int k::launch_l2norm_rows(const float* s, int ld, int col0, int rows, int width,
   return host::OK;
 }
 
-int k::launch_det_mean(const float* s, int ld, int col0, int B, int P, int width, float* det, cudaStream_t stream) {
+int k::launch_det_mean(const float* s, int ld, int col0, int B, int P, int width, float* inv_scratch, float* det,
+                       cudaStream_t stream) {
   if (B <= 0) return host::OK;
   if (width % 4 != 0 || ld % 4 != 0 || col0 % 4 != 0) return host::fail(host::ERR_INVALID, "det_mean: alignment");
-  dim3 grid(B, (width + 255) / 256);
-  det_mean_kernel<<<grid, 256, P * sizeof(float), stream>>>(s, ld, col0, P, width, det);
+  if (!inv_scratch) return host::fail(host::ERR_INVALID, "det_mean: scratch for %d row norms missing", B * P);
+  row_inv_norm_kernel<<<row_blocks(B * P), WARPS_PER_BLOCK * 32, 0, stream>>>(s, ld, col0, B * P, width, inv_scratch);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  dim3 grid(B, (width + 127) / 128);
+  det_mean_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(s, ld, col0, P, width, inv_scratch, det);
   AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }

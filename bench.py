@@ -63,11 +63,12 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None   # the timed region, wall clock: only samples inside it are reported
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -75,11 +76,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        self.rows = inside if inside else [r for _, r in self.rows[-3:]]
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -199,6 +208,11 @@ def main():
     assert b1 - b0 == B
     peaks = load_peaks()
 
+    # the clock sampler (a child nvidia-smi) starts before the weights are uploaded: its NVML start-up, which can stall
+    # the driver for ~100 ms, must not land in the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     eng = Engine(cfg, device=local_rank, max_batch=B, text=False, cta_group=args.cta_group)
     eng.load_state_dicts(synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0), None)
     anchors = synth.anchors(cfg, 1).cuda()
@@ -221,9 +235,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     launches0 = eng.launch_count
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evs[0].record()
@@ -231,6 +243,7 @@ def main():
         maps, scores = step(i)
         evs[i + 1].record()
     sync_all()
+    sampler.end()
     ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
