@@ -169,7 +169,11 @@ def _attention_ref(qkv, B, L, heads, causal):
 
 
 @pytest.mark.parametrize("B,L,heads,causal", [(1, 128, 1, False), (1, 577, 2, False), (2, 577, 16, False),
-                                               (3, 77, 12, True), (1, 200, 2, True), (2, 1370, 4, False)])
+                                               (3, 77, 12, True), (1, 200, 2, True), (2, 1370, 4, False),
+                                               # more work items than resident CTAs (2 x 148): the persistent loop,
+                                               # cross-item prefetch and the deferred output store
+                                               (12, 577, 16, False), (64, 77, 12, True), (5, 300, 16, True),
+                                               (3, 1370, 16, False)])
 def test_attention(B, L, heads, causal):
     ops = _ops()
     qkv = _rand_bf16(B * L, 3 * heads * 64, scale=1.5, seed=30)

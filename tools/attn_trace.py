@@ -7,7 +7,7 @@ B, L, H = 64, 577, 16
 qkv = (torch.randn(B * L, 3 * H * 64, device="cuda") * 1.5).to(torch.bfloat16)
 out = torch.empty(B * L, H * 64, device="cuda", dtype=torch.bfloat16)
 lib = _lib.load()
-for cta in (2000, 2001, 3003):
+for cta in (100, 101, 250):
     tr = torch.zeros(24 * 16, dtype=torch.int64, device="cuda")
     for _ in range(2):
         check(lib.aaclip_attention_trace(ptr(qkv), ptr(out), B, L, H, 0, ptr(tr), cta, cur_stream()))
@@ -15,7 +15,7 @@ for cta in (2000, 2001, 3003):
     t = tr.cpu().view(24, 16)[:, :10]
     t0 = int(t[0, 0])
     print(f"--- CTA {cta}: softmax warp0 stamps (cycles since first), per tile")
-    names = ["pre s_full", "s_full ok", "S loaded", "exp done", "o_full ok", "P stored", "arrived", "folded"]
+    names = ["tile top", "masked+max", "exp pass", "checked", "S next ld", "arrived", "ld landed", "-"]
     for s_ in range(8):
         print(f"{names[s_]:11s}", " ".join(f"{int(x) - t0:7d}" for x in t[s_]))
     print("MMA thread:")
