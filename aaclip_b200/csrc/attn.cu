@@ -2,26 +2,33 @@
 // [L, L] probability matrix the reference materialises (nn.MultiheadAttention slow path with
 // need_weights=True, model/transformer.py:200,237) never leaves the SM.
 //
-// PERSISTENT kernel: 2 CTAs per SM, each walks work items (128-row query tile, head, image) round robin; barriers,
-// the TMEM allocation and the K/V/P rings live for the whole launch and all pipelines run ACROSS item boundaries
-// (the next item's Q/K/V loads and first S = Q K^T tiles are in flight while the previous item's tail is still
-// being exponentiated; the previous item's output is normalised and stored after the next item's first tile).
+// The kernel's bound is the SFU: one MUFU.EX2 per score at 16 lanes/SM/clk (tools/micro/mufu_bench.cu: the
+// packed f16x2 / bf16x2 forms run at the same per-element rate), the tensor pipe is ~20 % busy.  Everything is
+// arranged to keep the four SFUs of an SM fed: FOUR small CTAs per SM (one softmax warp of each on every SMSP),
+// 32-key tiles so that a CTA needs only 53.5 KB smem / 128 TMEM columns / 80 registers, and a softmax loop whose
+// common case is a branch-free ~170-instruction stream per tile (instruction issue is the second bound).
+//
+// PERSISTENT: each CTA walks work items (128-row query tile, head, image) round robin; barriers, the TMEM
+// allocation and the K/V/P rings live for the whole launch and the pipelines run ACROSS item boundaries.
 // 6 warps; the two single-thread control roles sit in the HIGHEST warp ids (the SMSP arbiter favours high warp
-// ids, a delayed MMA issue or TMA request stalls all four softmax warps, and the control warps issue very little):
-//   warp 5      TMA producer: Q tile per item (double buffered), K_j / V_j tiles (64 keys) through 3-deep rings
-//   warp 4      TMEM allocator + tcgen05.mma issuer:  S_g = Q K_j^T (M128 N64 K64) into a double-buffered TMEM
-//               accumulator, always two tiles ahead of O += P_g V_j (M128 N64 K64; O double buffered per item)
-//   warps 0..3  softmax, thread == query row: tcgen05.ld of the 64 scores of the tile, then ONE streaming pass:
-//               exp2 on the SFU against a STALE stabiliser, row max / fp32 row sum / bf16 pack / swizzled smem store
-//               of P all in its shadow.  Only when the row max has grown by more than 2^8 since the stabiliser was
-//               adopted is O touched (tcgen05.ld / scale / tcgen05.st) and the tile redone; softmax is shift
-//               invariant and P <= 256 keeps bf16's relative precision, so the result is unchanged.
-// The kernel's bound is the SFU (one MUFU.EX2 per score, 16 lanes/SM, measured tools/micro/mufu_bench.cu);
-// POLY of every 8 exponentials can be evaluated on the FMA pipe instead (ptx::ex2_poly3).
+// ids, a late MMA issue or TMA request stalls all four softmax warps, and the control warps issue very little):
+//   warp 5      TMA producer: Q tile per item, K_j / V_j tiles (32 keys each) through 3- / 2-deep rings
+//   warp 4      TMEM allocator + tcgen05.mma issuer:  S_g = Q K_j^T (M128 N32 K64) into a double-buffered TMEM
+//               accumulator, always two tiles ahead of O += P_g V_j (M128 N64 K32)
+//   warps 0..3  softmax, thread == query row: tcgen05.ld of the tile's 32 scores, then ONE streaming pass:
+//               exp2 on the SFU against a STALE stabiliser, with row max / fp32 row sum / bf16 pack / swizzled smem
+//               store of P in its shadow; the next S tile is loaded from TMEM before the P hand-over.  Only when a
+//               row max has grown by more than 2^8 since the stabiliser was adopted is O touched (tcgen05.ld /
+//               scale / tcgen05.st) and the tile redone: softmax is shift invariant and P <= 256 keeps bf16's
+//               relative precision, so the result is unchanged.
+//               Item end: O / l -> bf16 -> the warp's own (idle) rows of the P buffer -> one TMA tile store through
+//               a rank-3 [B][L][W] tensor map (rows past the image's last token are clipped by the TMA unit).
+// P is ONE 128-row x 128-B swizzled buffer whose two 64-B halves hold alternate tiles (double buffering at no
+// extra smem); POLY of every 8 exponentials can be moved to the FMA pipe (ptx::ex2_poly3; measured slower here).
 // Operands come straight out of the fused QKV GEMM output qkv[B*L, 3*heads*64] through 2-D tensor maps: rows past
 // the image's last token are either the next image's tokens or TMA zero fill and are masked.  V tiles are consumed
-// as an MN-major B operand exactly as TMA lands them (no transpose).  The ragged last key tile (577 = 9*64 + 1)
-// only pays for the 32-key group(s) that hold valid keys.
+// as an MN-major B operand exactly as TMA lands them (no transpose).  The ragged last key tile (577 = 18*32 + 1)
+// only pays for one 16-key MMA step.
 //
 // mbarrier protocol notes (each was a silent-wrong-result bug once):
 //   * a parity wait can only tell the current phase from the previous one, so every wait below is on a barrier
@@ -29,11 +36,12 @@
 //   * p_full has four arrivers (one per softmax warp) that nothing else orders: two alternating instances, so
 //     two arrivals of one warp never land in one phase;
 //   * the tensor pipe retires one thread's MMAs in issue order and tcgen05.commit covers everything issued
-//     before it: "S_g complete" therefore implies "PV_{g-2} complete", which frees P buffer g & 1 without a wait.
+//     before it: "S_g complete" therefore implies "PV_{g-2} complete", which frees P half g & 1 without a wait.
 #include <limits.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 #include "internal.h"
 #include "ptx.cuh"
@@ -43,22 +51,27 @@ namespace attn {
 
 constexpr int D = 64;          // head dim
 constexpr int BQ = 128;        // query rows per work item
-constexpr int BKV = 64;        // keys per tile
-constexpr int NST = 3;         // K / V ring depth
+constexpr int BKV = 32;        // keys per tile
+constexpr int NSTK = 3;        // K ring depth (K_g is consumed two tiles ahead of V_g)
+constexpr int NSTV = 2;        // V ring depth
 constexpr int Q_BYTES = BQ * D * 2;      // 16 KB
-constexpr int KV_BYTES = BKV * D * 2;    //  8 KB
-constexpr int P_BYTES = BQ * BKV * 2;    // 16 KB: one 128B-swizzle atom column (64 keys) x 128 rows
+constexpr int KV_BYTES = BKV * D * 2;    //  4 KB
+constexpr int P_BYTES = BQ * 128;        // 16 KB: 128 rows x 128 B = two 32-key tiles side by side (double buffer)
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 256;           // S0 [0,64) S1 [64,128) O0 [128,192) O1 [192,256)
-constexpr int OFF_Q = 0;                           // 2 buffers
-constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
-constexpr int OFF_V = OFF_K + NST * KV_BYTES;
-constexpr int OFF_P = OFF_V + NST * KV_BYTES;      // 2 buffers: P_g is written while PV_{g-1} still reads
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;          // 114944 B: two CTAs per SM
+constexpr int TMEM_COLS = 128;           // S0 [0,32) S1 [32,64) O [64,128)
+
+template <int NQ>
+struct Lay {
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NQ * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + NSTK * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + NSTV * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;   // NQ=1: 53504 B (4 CTAs/SM), NQ=2: 69888 B (3 CTAs/SM)
+};
 
 struct Bars {
-  uint64_t q_full[2], q_empty[2], k_full[NST], v_full[NST], k_empty[NST], v_empty[NST], s_full[2], p_free[2],
+  uint64_t q_full[2], q_empty[2], k_full[NSTK], v_full[NSTV], k_empty[NSTK], v_empty[NSTV], s_full[2], p_free[2],
       p_full[2];
   uint32_t tmem_slot;
 };
@@ -66,27 +79,29 @@ static_assert(sizeof(Bars) <= 256, "barrier block");
 
 // work item -> (query tile, head, image); consecutive items share K/V (same head and image) for L2 reuse
 struct Item {
-  int q0, h, row_base, kv_end, n_kv;
+  int q0, h, b, row_base, kv_end, n_kv;
 };
 __device__ __forceinline__ Item decode_item(int w, int n_qt, int heads, int L, int causal) {
   Item it;
   const int qt = w % n_qt, r = w / n_qt;
   it.h = r % heads;
-  it.row_base = (r / heads) * L;   // first token row of this image in qkv / out
+  it.b = r / heads;
+  it.row_base = it.b * L;          // first token row of this image in qkv
   it.q0 = qt * BQ;
   it.kv_end = causal ? min(L, it.q0 + BQ) : L;   // keys [0, kv_end) can be visible to this query tile
   it.n_kv = (it.kv_end + BKV - 1) / BKV;
   return it;
 }
 
-template <bool TRACE_ON, int POLY>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool TRACE_ON, int POLY, int MINB, int NQ>
+__global__ void __launch_bounds__(THREADS, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                 __nv_bfloat16* __restrict__ out, int L, int heads, int causal, int n_items, int n_qt,
+                 const __grid_constant__ CUtensorMap tmO, int L, int heads, int causal, int n_items, int n_qt,
                  long long* trace, int trace_cta, float rescale_log2) {
+  using LY = Lay<NQ>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-B alignment
-  Bars* bars = reinterpret_cast<Bars*>(smem + OFF_BAR);
+  Bars* bars = reinterpret_cast<Bars*>(smem + LY::OFF_BAR);
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = ptx::lane_id();
   const int W = heads * D;
@@ -94,11 +109,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // optional clock64 trace of one CTA's SECOND work item (steady state; diagnostics):
   // [0..7][tile] softmax warp 0, [16..20][tile] MMA thread
   const bool tracing = TRACE_ON && (trace != nullptr) && (int(blockIdx.x) == trace_cta);
-#define TRACE(slot, tile) do { if (TRACE_ON && tracing && (tile) < 16) trace[(slot) * 16 + (tile)] = clock64(); } while (0)
+#define TRACE(slot, tile) do { if (TRACE_ON && tracing && (tile) < 32) trace[(slot) * 32 + (tile)] = clock64(); } while (0)
 
   if (warp == 5 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
+    ptx::prefetch_tmap(&tmO);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->q_full[i], 1);
       ptx::mbar_init(&bars->q_empty[i], 1);
@@ -106,12 +122,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::mbar_init(&bars->p_free[i], 1);
       ptx::mbar_init(&bars->p_full[i], 4);   // one arrive per softmax warp
     }
-    for (int i = 0; i < NST; ++i) {
-      ptx::mbar_init(&bars->k_full[i], 1);
-      ptx::mbar_init(&bars->v_full[i], 1);
-      ptx::mbar_init(&bars->k_empty[i], 1);
-      ptx::mbar_init(&bars->v_empty[i], 1);
-    }
+    for (int i = 0; i < NSTK; ++i) { ptx::mbar_init(&bars->k_full[i], 1); ptx::mbar_init(&bars->k_empty[i], 1); }
+    for (int i = 0; i < NSTV; ++i) { ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 4) {
@@ -126,23 +138,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 5) {
     // ===================================================== TMA producer
     if (ptx::elect_one()) {
-      int st = 0; uint32_t ph = 0;
+      int kst = 0, vst = 0; uint32_t kph = 0, vph = 0;
       uint32_t n = 0;   // item ordinal of this CTA
       for (int w = first; w < n_items; w += stride, ++n) {
         const Item it = decode_item(w, n_qt, heads, L, causal);
-        const uint32_t qb = n & 1u;
-        ptx::mbar_wait(&bars->q_empty[qb], ((n >> 1) & 1u) ^ 1u);
+        const uint32_t qb = n % NQ, qph = (n / NQ) & 1u;
+        ptx::mbar_wait(&bars->q_empty[qb], qph ^ 1u);
         ptx::mbar_arrive_expect_tx(&bars->q_full[qb], Q_BYTES);
-        ptx::tma_load_2d(smem + OFF_Q + qb * Q_BYTES, &tmQ, &bars->q_full[qb], it.h * D, it.row_base + it.q0);
+        ptx::tma_load_2d(smem + LY::OFF_Q + qb * Q_BYTES, &tmQ, &bars->q_full[qb], it.h * D, it.row_base + it.q0);
         for (int j = 0; j < it.n_kv; ++j) {
-          ptx::mbar_wait(&bars->k_empty[st], ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&bars->k_full[st], KV_BYTES);
-          ptx::tma_load_2d(smem + OFF_K + st * KV_BYTES, &tmKV, &bars->k_full[st], W + it.h * D, it.row_base + j * BKV);
-          ptx::mbar_wait(&bars->v_empty[st], ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&bars->v_full[st], KV_BYTES);
-          ptx::tma_load_2d(smem + OFF_V + st * KV_BYTES, &tmKV, &bars->v_full[st], 2 * W + it.h * D,
+          ptx::mbar_wait(&bars->k_empty[kst], kph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&bars->k_full[kst], KV_BYTES);
+          ptx::tma_load_2d(smem + LY::OFF_K + kst * KV_BYTES, &tmKV, &bars->k_full[kst], W + it.h * D,
                            it.row_base + j * BKV);
-          if (++st == NST) { st = 0; ph ^= 1u; }
+          if (++kst == NSTK) { kst = 0; kph ^= 1u; }
+          ptx::mbar_wait(&bars->v_empty[vst], vph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&bars->v_full[vst], KV_BYTES);
+          ptx::tma_load_2d(smem + LY::OFF_V + vst * KV_BYTES, &tmKV, &bars->v_full[vst], 2 * W + it.h * D,
+                           it.row_base + j * BKV);
+          if (++vst == NSTV) { vst = 0; vph ^= 1u; }
         }
       }
     }
@@ -155,29 +169,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // (| LBO field); stepping a tile / a 16-element K slice is an integer add on the low word.
       constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
       auto desc = [](uint32_t lo) { return (uint64_t(DESC_HI) << 32) | lo; };
-      const uint32_t q_lo = ((ptx::smem_u32(smem + OFF_Q) & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t k_lo = ((ptx::smem_u32(smem + OFF_K) & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t p_lo = ((ptx::smem_u32(smem + OFF_P) & 0x3FFFFu) >> 4) | (1u << 16);
-      const uint32_t v_lo = ((ptx::smem_u32(smem + OFF_V) & 0x3FFFFu) >> 4) | ((1024u >> 4) << 16);
+      const uint32_t q_lo = ((ptx::smem_u32(smem + LY::OFF_Q) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t k_lo = ((ptx::smem_u32(smem + LY::OFF_K) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t p_lo = ((ptx::smem_u32(smem + LY::OFF_P) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t v_lo = ((ptx::smem_u32(smem + LY::OFF_V) & 0x3FFFFu) >> 4) | ((1024u >> 4) << 16);
       // ---- S cursor: runs two tiles ahead of the PV cursor, across item boundaries
       int s_w = first, s_j = 0, s_st = 0; uint32_t s_ph = 0, s_n = 0, s_g = 0;
       int s_nkv = (s_w < n_items) ? decode_item(s_w, n_qt, heads, L, causal).n_kv : 0;
       auto issue_s = [&]() {   // S tile s_g -> TMEM S[s_g & 1]
         if (s_w >= n_items) return;
-        const uint32_t qb = s_n & 1u;
-        if (s_j == 0) ptx::mbar_wait(&bars->q_full[qb], (s_n >> 1) & 1u);
+        const uint32_t qb = s_n % NQ;
+        if (s_j == 0) ptx::mbar_wait(&bars->q_full[qb], (s_n / NQ) & 1u);
         ptx::mbar_wait(&bars->k_full[s_st], s_ph);
         ptx::tc_fence_after();
         const uint32_t qd = q_lo + qb * (Q_BYTES >> 4);
         const uint32_t kb = k_lo + uint32_t(s_st) * (KV_BYTES >> 4);
-        const uint32_t t_s = tmem_base + (s_g & 1u) * 64u;
+        const uint32_t t_s = tmem_base + (s_g & 1u) * uint32_t(BKV);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
           ptx::mma_f16_ss<1>(t_s, desc(qd + k * 2), desc(kb + k * 2), idesc_s, k != 0 ? 1u : 0u);
         ptx::mma_commit(&bars->s_full[s_g & 1u]);
         ptx::mma_commit(&bars->k_empty[s_st]);
         ++s_g;
-        if (++s_st == NST) { s_st = 0; s_ph ^= 1u; }
+        if (++s_st == NSTK) { s_st = 0; s_ph ^= 1u; }
         if (++s_j == s_nkv) {          // last S tile of the item: its Q buffer is free once these MMAs retire
           ptx::mma_commit(&bars->q_empty[qb]);
           s_w += stride; ++s_n; s_j = 0;
@@ -188,33 +202,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       issue_s();
       // ---- PV cursor
       int st = 0; uint32_t ph = 0, g = 0, n = 0;
+      const uint32_t t_o = tmem_base + 2u * BKV;
       for (int w = first; w < n_items; w += stride, ++n) {
         const Item it = decode_item(w, n_qt, heads, L, causal);
-        const uint32_t t_o = tmem_base + 128u + (n & 1u) * 64u;
         for (int j = 0; j < it.n_kv; ++j, ++g) {
           if (n == 1) TRACE(16, j);
-          ptx::mbar_wait(&bars->p_full[g & 1u], (g >> 1) & 1u);  // P_g in smem, S[g&1] drained, O rescaled if needed
+          ptx::mbar_wait(&bars->p_full[g & 1u], (g >> 1) & 1u);  // P_g in smem, S[g&1] drained, O rescaled / drained
           if (n == 1) TRACE(17, j);
           ptx::mbar_wait(&bars->v_full[st], ph);
           ptx::tc_fence_after();
           if (n == 1) TRACE(18, j);
-          const uint32_t pb = p_lo + (g & 1u) * (P_BYTES >> 4);
+          // A: P tile g = key columns [(g&1)*32, +32) of the 128-B swizzled P rows: +64 B per tile, +32 B per 16 keys
+          // B: V tile as TMA landed it (MN-major), 16 keys = 16 rows x 128 B = +2048 B
+          const uint32_t pb = p_lo + (g & 1u) * 4u;
           const uint32_t vb = v_lo + uint32_t(st) * (KV_BYTES >> 4);
           const uint32_t acc0 = j > 0 ? 1u : 0u;   // O accumulates over the key tiles of one item
-          // A: P tile = one 64-key swizzle atom column (128 rows x 128 B), 16 keys = +32 B;
-          // B: V tile as TMA landed it (MN-major), 16 keys = 16 rows x 128 B = +2048 B
-          if (j + 1 < it.n_kv || it.kv_end - j * BKV >= BKV) {
-#pragma unroll
-            for (int k = 0; k < BKV / 16; ++k)
-              ptx::mma_f16_ss<1>(t_o, desc(pb + k * 2), desc(vb + k * 128), idesc_o, k != 0 ? 1u : acc0);
-          } else {   // ragged last tile: skip 16-key groups that are fully hidden
-            const int ksteps = (it.kv_end - j * BKV + 15) >> 4;
-            for (int k = 0; k < ksteps; ++k)
-              ptx::mma_f16_ss<1>(t_o, desc(pb + k * 2), desc(vb + k * 128), idesc_o, k != 0 ? 1u : acc0);
-          }
+          const int ksteps = min(BKV / 16, (it.kv_end - j * BKV + 15) >> 4);   // ragged last tile: skip hidden keys
+          for (int k = 0; k < ksteps; ++k)
+            ptx::mma_f16_ss<1>(t_o, desc(pb + k * 2), desc(vb + k * 128), idesc_o, k != 0 ? 1u : acc0);
           ptx::mma_commit(&bars->v_empty[st]);
-          ptx::mma_commit(&bars->p_free[g & 1u]);   // PV_g has landed in O and has finished reading P[g & 1]
-          if (++st == NST) { st = 0; ph ^= 1u; }
+          ptx::mma_commit(&bars->p_free[g & 1u]);   // PV_g has landed in O and has finished reading P half g & 1
+          if (++st == NSTV) { st = 0; ph ^= 1u; }
           if (n == 1) TRACE(19, j);
           issue_s();                                // S tile g + 2 (S[g & 1] was drained before p_full completed)
           if (n == 1) TRACE(20, j);
@@ -226,130 +234,111 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t quarter = warp & 3u;
     const int row = int(quarter * 32u + lane);
     const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16);
+    const uint32_t t_o = t_lane + 2u * BKV;
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     const float RESCALE_LOG2 = rescale_log2;       // lazy rescale: tolerate p up to 2^8 before touching O
-    uint8_t* p_row = smem + OFF_P + row * 128;
+    uint8_t* p_row = smem + LY::OFF_P + row * 128;
+    uint8_t* p_warp = smem + LY::OFF_P + quarter * 32u * 128u;   // this warp's 32 rows x 128 B (output staging)
     const uint32_t sw = uint32_t(row & 7);
-    uint32_t sv[64];                               // raw scores of the current tile (this thread's row)
-    uint32_t (&sv_lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[0]);
-    uint32_t (&sv_hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sv[32]);
+    // shared-space address of the 16-B chunk that holds keys [8c, 8c+8) of this row's P line (128B swizzle)
+    uint32_t p_addr[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) p_addr[ch] = ptx::smem_u32(p_row) + ((uint32_t(ch) ^ sw) << 4);
+    uint32_t sv[BKV];                              // raw scores of the current tile (this thread's row)
 
-    // issue the TMEM loads of S tile g (no wait): 32 or 64 columns depending on how many keys the tile holds
-    auto load_scores = [&](uint32_t g, int tile_keys) {
-      const uint32_t t_s = t_lane + (g & 1u) * 64u;
-      ptx::tmem_ld_32x32b_x32(t_s, sv_lo);
-      if (tile_keys > 32) ptx::tmem_ld_32x32b_x32(t_s + 32, sv_hi);
-    };
+    auto load_scores = [&](uint32_t g) { ptx::tmem_ld_32x32b_x32(t_lane + (g & 1u) * uint32_t(BKV), sv); };
     // hidden keys -> -inf -> p = 0 (last key tile / causal diagonal only)
     auto mask_scores = [&](int kv0, int q0, int qi) {
-      if ((kv0 + BKV > L) || (causal && kv0 + BKV > q0 + 1)) {
-        int limit = L - kv0;                            // this row sees keys [0, limit) of the tile
-        if (causal) limit = min(limit, qi - kv0 + 1);   // CLIP text mask (model/model.py:172): keys > qi hidden
+      int limit = L - kv0;                            // this row sees keys [0, limit) of the tile
+      if (causal) limit = min(limit, qi - kv0 + 1);   // CLIP text mask (model/model.py:172): keys > qi hidden
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= limit) sv[i] = 0xff800000u;
-      }
+      for (int i = 0; i < BKV; ++i)
+        if (i >= limit) sv[i] = 0xff800000u;
     };
-    // One streaming pass over the tile: p = exp2((s - m) * c) -> bf16 -> swizzled smem (16 B per 8 keys, stored as
-    // soon as packed), fp32 row sum and the tile's row max, all in one instruction stream so that the FMNMX /
-    // FADD / F2FP / STS work hides under the SFU (MUFU.EX2) latency instead of forming serial phases.
-    auto exp_pass = [&](uint8_t* pr, float mc, int n_groups, float& rowsum, float& rowmax) {
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    // One streaming pass over NG 8-key groups of the tile: p = exp2((s - m) * c) -> bf16 -> swizzled smem (16 B per
+    // group, stored as soon as packed), fp32 row sum and the tile's row max, all in one branch-free instruction
+    // stream so that the FMNMX / FADD / F2FP / STS work hides under the SFU (MUFU.EX2) latency.
+    // `half` selects the tile's 64-B half of the 128-B P row (chunks half*4 .. half*4+3).
+    auto exp_pass = [&](auto ng_tag, uint32_t half, float mc, float& rowsum, float& rowmax) {
+      constexpr int NG = decltype(ng_tag)::value;
+      float rs2[2] = {0.f, 0.f};
+      float mx2[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) {
-        if (g8 < n_groups) {
-          float e[8];
+      for (int g8 = 0; g8 < NG; ++g8) {
+        float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float x = fmaf(__uint_as_float(sv[8 * g8 + i]), c, -mc);
-            e[i] = (i >= 8 - POLY) ? ptx::ex2_poly3(x) : ptx::ex2_approx(x);
-          }
-          mx4[g8 & 3] = fmaxf(mx4[g8 & 3],
-                              fmaxf(fmaxf(__uint_as_float(sv[8 * g8 + 0]), __uint_as_float(sv[8 * g8 + 1])),
-                                    fmaxf(__uint_as_float(sv[8 * g8 + 2]), __uint_as_float(sv[8 * g8 + 3]))));
-          mx4[(g8 + 2) & 3] = fmaxf(mx4[(g8 + 2) & 3],
-                                    fmaxf(fmaxf(__uint_as_float(sv[8 * g8 + 4]), __uint_as_float(sv[8 * g8 + 5])),
-                                          fmaxf(__uint_as_float(sv[8 * g8 + 6]), __uint_as_float(sv[8 * g8 + 7]))));
-          rs4[g8 & 3] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          ptx::st_shared_v4(pr + ((uint32_t(g8) ^ sw) << 4), ptx::pack_bf16x2(e[0], e[1]), ptx::pack_bf16x2(e[2], e[3]),
-                            ptx::pack_bf16x2(e[4], e[5]), ptx::pack_bf16x2(e[6], e[7]));
+        for (int i = 0; i < 8; ++i) {
+          const float x = fmaf(__uint_as_float(sv[8 * g8 + i]), c, -mc);
+          e[i] = (i >= 8 - POLY) ? ptx::ex2_poly3(x) : ptx::ex2_approx(x);
         }
+        mx2[0] = fmaxf(mx2[0], fmaxf(fmaxf(__uint_as_float(sv[8 * g8 + 0]), __uint_as_float(sv[8 * g8 + 1])),
+                                     fmaxf(__uint_as_float(sv[8 * g8 + 2]), __uint_as_float(sv[8 * g8 + 3]))));
+        mx2[1] = fmaxf(mx2[1], fmaxf(fmaxf(__uint_as_float(sv[8 * g8 + 4]), __uint_as_float(sv[8 * g8 + 5])),
+                                     fmaxf(__uint_as_float(sv[8 * g8 + 6]), __uint_as_float(sv[8 * g8 + 7]))));
+        rs2[g8 & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        const uint32_t a = half ? p_addr[4 + g8] : p_addr[g8];
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ptx::pack_bf16x2(e[0], e[1])),
+                     "r"(ptx::pack_bf16x2(e[2], e[3])), "r"(ptx::pack_bf16x2(e[4], e[5])),
+                     "r"(ptx::pack_bf16x2(e[6], e[7])) : "memory");
       }
-      rowsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
-      rowmax = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      rowsum = rs2[0] + rs2[1];
+      rowmax = fmaxf(mx2[0], mx2[1]);
     };
-    // normalise O of a finished item by its row sum and store it (deferred: runs after the next item's first tile)
-    auto store_output = [&](uint32_t t_o, uint32_t g_last, float l, __nv_bfloat16* orow, bool valid) {
-      // PV_{g_last} complete.  The next completion of this barrier needs P_{g_last+2}, which this warp has not
-      // produced yet, so the barrier is at most one phase ahead: the parity wait is unambiguous.
-      ptx::mbar_wait(&bars->p_free[g_last & 1u], (g_last >> 1) & 1u);
-      ptx::tc_fence_after();
-      const float inv = 1.0f / l;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_o + hh * 32, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + hh * 32);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 wv;
-            wv.x = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]) * inv, __uint_as_float(v[q4 * 8 + 1]) * inv);
-            wv.y = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]) * inv, __uint_as_float(v[q4 * 8 + 3]) * inv);
-            wv.z = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]) * inv, __uint_as_float(v[q4 * 8 + 5]) * inv);
-            wv.w = ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]) * inv, __uint_as_float(v[q4 * 8 + 7]) * inv);
-            dst[q4] = wv;
-          }
-        }
-      }
-    };
+    using NG4 = std::integral_constant<int, 4>;
+    using NG2 = std::integral_constant<int, 2>;
 
     const bool tr = TRACE_ON && tracing && warp == 0 && lane == 0;
-#define TRS(slot) do { if (TRACE_ON && tr && n == 1 && j < 16) trace[(slot) * 16 + j] = clock64(); } while (0)
-    // pending output of the previous item
-    bool pend = false, pend_valid = false;
-    uint32_t pend_to = 0, pend_g = 0;
-    float pend_l = 1.f;
-    __nv_bfloat16* pend_row = nullptr;
+#define TRS(slot) do { if (TRACE_ON && tr && n == 1 && j < 32) trace[(slot) * 32 + j] = clock64(); } while (0)
+    bool store_pending = false;   // a TMA store is still reading this warp's P rows (lane 0 owns the bulk group)
 
     uint32_t g = 0, n = 0;
     if (first < n_items) {
-      const Item it0 = decode_item(first, n_qt, heads, L, causal);
       ptx::mbar_wait(&bars->s_full[0], 0);
       ptx::tc_fence_after();
-      load_scores(0, min(BKV, it0.kv_end));
+      load_scores(0);
       ptx::tmem_ld_wait();
     }
     for (int w = first; w < n_items; w += stride, ++n) {
       const Item it = decode_item(w, n_qt, heads, L, causal);
       const int qi = it.q0 + row;
-      const uint32_t t_o = t_lane + 128u + (n & 1u) * 64u;
       float m_used = 0.f, l = 0.f;                   // stabiliser in use (<= true running max + 2^8), row sum
-      // tile geometry of the NEXT item's first tile (for the prefetch across the item boundary)
-      const int w_next = w + stride;
-      const int next_first_keys = (w_next < n_items) ? min(BKV, decode_item(w_next, n_qt, heads, L, causal).kv_end) : 0;
+      const bool more_items = (w + stride < n_items);
+      // tiles [1, j_fast) are complete and unmasked for every row of the item and are not its last tile (so a
+      // next S tile always exists): they take the lean path
+      const int j_fast = min(it.n_kv - 1, (causal ? min(L, it.q0 + 1) : L) / BKV);
 
-      for (int j = 0; j < it.n_kv; ++j, ++g) {
+      // One key tile.  FAST: 32 visible keys for every row, not the item's first tile.  Everything else (first tile:
+      // adopt the true row max and wait for the previous output store; ragged / causal tiles: mask, fewer groups)
+      // goes through the general form.
+      auto tile = [&](auto fast_tag, int j) {
+        constexpr bool FAST = decltype(fast_tag)::value;
         TRS(0);
         const int kv0 = j * BKV;
-        const int n_groups = min(BKV, it.kv_end - kv0) > 32 ? 8 : 4;   // 8-key groups holding visible keys
-        uint8_t* pr = p_row + (g & 1u) * P_BYTES;
-        // P buffer g & 1 was last read by PV_{g-2}: free, because S_g (seen complete) was issued after it.
-        mask_scores(kv0, it.q0, qi);
-        if (j == 0) {   // first tile: adopt its true row max (a fully hidden row - rows >= L, never stored - uses 0)
-          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const uint32_t half = g & 1u;
+        // P half g & 1 was last read by PV_{g-2}: free, because S_g (seen complete) was issued after it.
+        bool four = true;   // 8-key groups to exponentiate: whole 16-key MMA k-steps that hold visible keys
+        if constexpr (!FAST) {
+          four = (it.kv_end - kv0) > 16;
+          if ((kv0 + BKV > L) || (causal && kv0 + BKV > it.q0 + 1)) mask_scores(kv0, it.q0, qi);
+          if (j == 0) {   // adopt the true row max (a fully hidden row - rows >= L, never stored - uses 0)
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int i = 0; i < 64; i += 2)
-            if (i < 8 * n_groups)
-              mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
-          const float mt0 = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-          m_used = (mt0 == -INFINITY) ? 0.f : mt0;
+            for (int i = 0; i < BKV; i += 2)
+              if (i < 16 || four)
+                mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+            const float mt0 = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            m_used = (mt0 == -INFINITY) ? 0.f : mt0;
+            if (store_pending) {   // the previous item's output store must have finished reading these P rows
+              if (lane == 0) ptx::bulk_wait_read<0>();
+              __syncwarp();
+              store_pending = false;
+            }
+          }
         }
         TRS(1);
         float rs, mt;
-        exp_pass(pr, m_used * c, n_groups, rs, mt);
+        if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs, mt);
+        else exp_pass(NG2{}, half, m_used * c, rs, mt);
         TRS(2);
         // ---- stale stabiliser check: only when some row's max grew by more than 2^RESCALE is O touched
         const bool grow = (mt - m_used) * c > RESCALE_LOG2;
@@ -362,7 +351,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             // of PV_{g-1} or one past it.
             ptx::mbar_wait(&bars->p_free[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
             ptx::tc_fence_after();
-#pragma unroll
+#pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
               uint32_t v[32];
               ptx::tmem_ld_32x32b_x32(t_o + hh * 32, v);
@@ -376,39 +365,71 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           l *= alpha;
           m_used = m_next;
           // redo the tile against the new stabiliser (S_g is still in TMEM: it is released by the p_full arrive)
-          load_scores(g, min(BKV, it.kv_end - kv0));
+          load_scores(g);
           ptx::tmem_ld_wait();
-          mask_scores(kv0, it.q0, qi);
-          exp_pass(pr, m_used * c, n_groups, rs, mt);
+          if (!FAST && ((kv0 + BKV > L) || (causal && kv0 + BKV > it.q0 + 1))) mask_scores(kv0, it.q0, qi);
+          if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs, mt);
+          else exp_pass(NG2{}, half, m_used * c, rs, mt);
         }
         l += rs;
         TRS(3);
         // ---- prefetch the next S tile (possibly the next item's first) while the P hand-over is in flight
-        const bool last_tile = (j + 1 == it.n_kv);
-        const int next_keys = last_tile ? next_first_keys : min(BKV, it.kv_end - (kv0 + BKV));
-        if (next_keys > 0) {
-          ptx::mbar_wait(&bars->s_full[(g + 1) & 1u], ((g + 1) >> 1) & 1u);
+        if (FAST || j + 1 < it.n_kv || more_items) {
+          ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
           ptx::tc_fence_after();
-          load_scores(g + 1, next_keys);
+          load_scores(g + 1);
         }
         TRS(4);
         ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->p_full[g & 1u]);   // P_g in smem, S[g & 1] drained, O rescaled
+        if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
         TRS(5);
         ptx::tmem_ld_wait();
-        // ---- the previous item's output, one tile late: its last PV has long landed by now
-        if (j == 0 && pend) {
-          store_output(pend_to, pend_g, pend_l, pend_row, pend_valid);
-          pend = false;
-        }
         TRS(6);
+        ++g;
+      };
+
+      int j = 0;
+      tile(std::false_type{}, j++);
+#pragma unroll 1
+      for (; j < j_fast; ++j) tile(std::true_type{}, j);
+#pragma unroll 1
+      for (; j < it.n_kv; ++j) tile(std::false_type{}, j);
+
+      // ---- item done: O / l -> bf16 -> this warp's (now idle) P rows -> one TMA tile store (rows >= L are clipped
+      //      by the per-image tensor map).  PV_{g-1} complete means every PV of the item is (issue order).
+      {
+        const uint32_t g_last = g - 1;
+        // the next completion of this barrier needs P_{g_last+2}, which this warp has not produced: unambiguous
+        ptx::mbar_wait(&bars->p_free[g_last & 1u], (g_last >> 1) & 1u);
+        ptx::tc_fence_after();
+        const float inv = 1.0f / l;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_o + hh * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            ptx::st_shared_v4(p_row + ((uint32_t(hh * 4 + q4) ^ sw) << 4),
+                              ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]) * inv, __uint_as_float(v[q4 * 8 + 1]) * inv),
+                              ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]) * inv, __uint_as_float(v[q4 * 8 + 3]) * inv),
+                              ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]) * inv, __uint_as_float(v[q4 * 8 + 5]) * inv),
+                              ptx::pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]) * inv, __uint_as_float(v[q4 * 8 + 7]) * inv));
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();     // O has been read: orders the TMEM loads before the next p_full arrive
+        __syncwarp();
+        const int r0 = it.q0 + int(quarter) * 32;
+        if (lane == 0 && r0 < L) {
+          ptx::tma_store_3d(&tmO, p_warp, it.h * D, r0, it.b);
+          ptx::bulk_commit();
+        }
+        store_pending = true;
       }
-      pend = true; pend_to = t_o; pend_g = g - 1; pend_l = l; pend_valid = (qi < L);
-      pend_row = out + (size_t)(it.row_base + qi) * W + it.h * D;
     }
-    if (pend) store_output(pend_to, pend_g, pend_l, pend_row, pend_valid);
+    if (store_pending && lane == 0) ptx::bulk_wait<0>();   // smem must outlive the last store's read
   }
 
   __syncwarp();
@@ -419,42 +440,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace attn
 
-constexpr int ATTN_POLY_DEFAULT = 0;
 namespace {
 long long* g_trace = nullptr;   // diagnostics only (aaclip_attention_trace)
 int g_trace_cta = -1;
+
+typedef void (*AttnKern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, int, int, long long*,
+                         int, float);
+struct AttnVariant { AttnKern fn; int smem; int ctas_per_sm; };
+
+template <int POLY>
+AttnVariant pick(int minb, bool trace) {
+  if (trace) return {attn::attention_kernel<true, 0, 3, 2>, attn::Lay<2>::SMEM_BYTES, 3};
+  if (minb == 4) return {attn::attention_kernel<false, POLY, 4, 1>, attn::Lay<1>::SMEM_BYTES, 4};
+  return {attn::attention_kernel<false, POLY, 3, 2>, attn::Lay<2>::SMEM_BYTES, 3};
 }
+}  // namespace
 
 int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int causal, cudaStream_t stream) {
   if (B <= 0) return host::OK;
   if (L <= 0 || heads <= 0) return host::fail(host::ERR_INVALID, "attention: L=%d heads=%d", L, heads);
   const int W = heads * attn::D;
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmO;
   int rc = host::make_tmap_2d(&tmQ, qkv, (uint64_t)B * L, 3 * W, 3 * W, attn::BQ);
   if (rc) return rc;
   rc = host::make_tmap_2d(&tmKV, qkv, (uint64_t)B * L, 3 * W, 3 * W, attn::BKV);
   if (rc) return rc;
-  // AACLIP_ATTN_POLY=<0..4> (diagnostics): exponentials per 8 evaluated on the FMA pipe instead of the SFU
-  static int poly = getenv("AACLIP_ATTN_POLY") ? atoi(getenv("AACLIP_ATTN_POLY")) : ATTN_POLY_DEFAULT;
-  static float rescale = getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f;
-  typedef void (*Kern)(const CUtensorMap, const CUtensorMap, __nv_bfloat16*, int, int, int, int, int, long long*, int,
-                       float);
-  Kern kern = nullptr;
-  if (g_trace) kern = attn::attention_kernel<true, 0>;
-  else switch (poly) {
-    case 0: kern = attn::attention_kernel<false, 0>; break;
-    case 1: kern = attn::attention_kernel<false, 1>; break;
-    case 2: kern = attn::attention_kernel<false, 2>; break;
-    case 3: kern = attn::attention_kernel<false, 3>; break;
-    case 4: kern = attn::attention_kernel<false, 4>; break;
-    default: return host::fail(host::ERR_INVALID, "AACLIP_ATTN_POLY=%d out of range [0,4]", poly);
+  {   // output [B][L][W] bf16 as a rank-3 map: a 32-row store box is clipped at each image's last token
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)L, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)W * 2, (uint64_t)L * W * 2};
+    const uint32_t box[3] = {64, 32, 1};
+    rc = host::make_tmap_bf16(&tmO, out, 3, dims, strides, box);
+    if (rc) return rc;
   }
-  static Kern configured[8] = {nullptr};
+  // diagnostics: AACLIP_ATTN_POLY=<0..2> exponentials per 8 evaluated on the FMA pipe instead of the SFU;
+  //              AACLIP_ATTN_CTAS=<3|4> resident CTAs per SM (4: single Q buffer, 80 registers)
+  static int poly = getenv("AACLIP_ATTN_POLY") ? atoi(getenv("AACLIP_ATTN_POLY")) : 0;
+  static int minb = getenv("AACLIP_ATTN_CTAS") ? atoi(getenv("AACLIP_ATTN_CTAS")) : 4;
+  static float rescale = getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f;
+  AttnVariant v;
+  switch (poly) {
+    case 0: v = pick<0>(minb, g_trace != nullptr); break;
+    case 1: v = pick<1>(minb, g_trace != nullptr); break;
+    case 2: v = pick<2>(minb, g_trace != nullptr); break;
+    default: return host::fail(host::ERR_INVALID, "AACLIP_ATTN_POLY=%d out of range [0,2]", poly);
+  }
+  static AttnKern configured[16] = {nullptr};
   bool seen = false;
-  for (Kern kk : configured) seen = seen || (kk == kern);
+  for (AttnKern kk : configured) seen = seen || (kk == v.fn);
   if (!seen) {
-    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    for (Kern& kk : configured) if (!kk) { kk = kern; break; }
+    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+    for (AttnKern& kk : configured) if (!kk) { kk = v.fn; break; }
   }
   int dev = 0;
   AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -462,9 +497,9 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   const long long items = (long long)n_qt * heads * B;
   if (items > INT_MAX) return host::fail(host::ERR_INVALID, "attention: %lld work items", items);
   const int sms = host::sm_count(dev);
-  const int grid = (int)std::min<long long>(items, 2LL * (sms > 0 ? sms : 148));
-  kern<<<grid, attn::THREADS, attn::SMEM_BYTES, stream>>>(tmQ, tmKV, static_cast<__nv_bfloat16*>(out), L, heads, causal,
-                                                          (int)items, n_qt, g_trace, g_trace_cta, rescale);
+  const int grid = (int)std::min<long long>(items, (long long)v.ctas_per_sm * (sms > 0 ? sms : 148));
+  v.fn<<<grid, attn::THREADS, v.smem, stream>>>(tmQ, tmKV, tmO, L, heads, causal, (int)items, n_qt, g_trace, g_trace_cta,
+                                                rescale);
   AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }
@@ -475,7 +510,7 @@ extern "C" int aaclip_attention(const void* qkv, void* out, int B, int L, int he
 
 // Diagnostics: like aaclip_attention, but CTA number `cta` also records clock64() stamps of its softmax warp 0
 // (slots 0..7) and of its MMA-issuing thread (slots 16..20) per key tile of its second work item into
-// trace[slot * 16 + tile] (device memory, >= 24 * 16 int64).  Used to study the pipeline; not part of the hot path.
+// trace[slot * 32 + tile] (device memory, >= 24 * 32 int64).  Used to study the pipeline; not part of the hot path.
 extern "C" int aaclip_attention_trace(const void* qkv, void* out, int B, int L, int heads, int causal, long long* trace,
                                       int cta, void* stream) {
   g_trace = trace; g_trace_cta = cta;

@@ -75,11 +75,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung
-// GPU.  The bound is on retries (each retry sleeps in hardware), far beyond any legitimate wait.
+// GPU.  The bound is ~2.5 s of SM clocks (only the retry path reads the clock), far beyond any legitimate wait.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t tries = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++tries > 50000000u) { __trap(); }
+    if (clock64() - t0 > 4000000000LL) { __trap(); }
   }
 }
 
@@ -117,6 +118,10 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
