@@ -52,8 +52,8 @@ namespace attn {
 constexpr int D = 64;          // head dim
 constexpr int BQ = 128;        // query rows per work item
 constexpr int BKV = 32;        // keys per tile
-constexpr int NSTK = 3;        // K ring depth (K_g is consumed two tiles ahead of V_g)
-constexpr int NSTV = 2;        // V ring depth
+constexpr int NSTK = 2;        // K ring depth (K_g is consumed as soon as it lands, two tiles ahead of V_g)
+constexpr int NSTV = 3;        // V ring depth (V_g waits for P_g: its slot is held two tiles longer)
 constexpr int Q_BYTES = BQ * D * 2;      // 16 KB
 constexpr int KV_BYTES = BKV * D * 2;    //  4 KB
 constexpr int P_BYTES = BQ * 128;        // 16 KB: 128 rows x 128 B = two 32-key tiles side by side (double buffer)
@@ -134,6 +134,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_slot);
+  ptx::grid_dep_sync();   // everything above overlapped the previous kernel's tail
 
   if (warp == 5) {
     // ===================================================== TMA producer
@@ -498,9 +499,8 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   if (items > INT_MAX) return host::fail(host::ERR_INVALID, "attention: %lld work items", items);
   const int sms = host::sm_count(dev);
   const int grid = (int)std::min<long long>(items, (long long)v.ctas_per_sm * (sms > 0 ? sms : 148));
-  v.fn<<<grid, attn::THREADS, v.smem, stream>>>(tmQ, tmKV, tmO, L, heads, causal, (int)items, n_qt, g_trace, g_trace_cta,
-                                                rescale);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(v.fn, dim3(grid), dim3(attn::THREADS), (size_t)v.smem, stream, tmQ, tmKV, tmO, L, heads,
+                                 causal, (int)items, n_qt, g_trace, g_trace_cta, rescale));
   return host::OK;
 }
 

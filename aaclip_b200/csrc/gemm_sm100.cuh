@@ -272,6 +272,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  ptx::grid_dep_sync();   // everything above overlapped the previous kernel's tail
 
   if (warp == 8) {
     // ===================================================== TMA producer

@@ -26,6 +26,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 patch_dots_kernel(SegPtrs seg, int n_levels, const float* __restrict__ anchors, int anchors_batched, int rows, int P,
                   int E, float* __restrict__ dots) {
+  ptx::grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -84,6 +85,7 @@ constexpr int HEAD_THREADS = 256;
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int S, int mode,
                  float* __restrict__ maps) {
+  ptx::grid_dep_sync();
   extern __shared__ float sm[];
   const int P = G * G;
   float* m = sm;                 // [C][G][G]  per-patch scalars
@@ -201,6 +203,7 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
 // scores[b] = (<det[b], anchors[:,1]> + 1) / 2      (test.py:83-84)
 __global__ void scores_kernel(const float* __restrict__ det, const float* __restrict__ anchors, int anchors_batched,
                               int B, int E, float* __restrict__ scores) {
+  ptx::grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -216,6 +219,7 @@ __global__ void scores_kernel(const float* __restrict__ det, const float* __rest
 // of anchors [width, 2].  One block; n is a handful of prompt sentences.
 __global__ void __launch_bounds__(256)
 text_anchor_kernel(const float* __restrict__ emb, int n, int width, float* __restrict__ anchors, int col) {
+  ptx::grid_dep_sync();
   extern __shared__ float sh[];  // [n] inverse row norms, then [8] partial sums
   float* inv = sh;
   float* part = sh + n;
@@ -258,10 +262,11 @@ int k::launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, 
   const int rows = B * P;
   const int blocks = (rows + 7) / 8;
   if (seg_is_bf16)
-    patch_dots_kernel<true><<<blocks, 256, 0, stream>>>(sp, n_levels, anchors, anchors_batched, rows, P, E, dots);
+    AACLIP_CUDA_CHECK(host::launch(patch_dots_kernel<true>, dim3(blocks), dim3(256), 0, stream, sp, n_levels, anchors,
+                                   anchors_batched, rows, P, E, dots));
   else
-    patch_dots_kernel<false><<<blocks, 256, 0, stream>>>(sp, n_levels, anchors, anchors_batched, rows, P, E, dots);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+    AACLIP_CUDA_CHECK(host::launch(patch_dots_kernel<false>, dim3(blocks), dim3(256), 0, stream, sp, n_levels, anchors,
+                                   anchors_batched, rows, P, E, dots));
   return host::OK;
 }
 
@@ -278,15 +283,14 @@ int k::launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_
     configured = smem;
   }
   dim3 grid((S + BAND - 1) / BAND, B, mode == AACLIP_HEAD_TRAIN_SOFTMAX ? n_levels : 1);
-  head_maps_kernel<<<grid, HEAD_THREADS, smem, stream>>>(dots, n_levels, B, G, S, mode, maps);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(head_maps_kernel, grid, dim3(HEAD_THREADS), smem, stream, dots, n_levels, B, G, S, mode, maps));
   return host::OK;
 }
 
 int k::launch_scores(const float* det, const float* anchors, int anchors_batched, int B, int E, float* scores,
                      cudaStream_t stream) {
-  scores_kernel<<<(B + 7) / 8, 256, 0, stream>>>(det, anchors, anchors_batched, B, E, scores);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(scores_kernel, dim3((B + 7) / 8), dim3(256), 0, stream, det, anchors, anchors_batched, B, E,
+                                 scores));
   return host::OK;
 }
 

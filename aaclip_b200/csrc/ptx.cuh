@@ -38,6 +38,16 @@ __device__ __forceinline__ void cluster_wait() {
 }
 __device__ __forceinline__ void cluster_sync() { cluster_arrive(); cluster_wait(); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library starts with grid_dep_sync() before it touches global memory: wait until the
+// preceding kernel in the stream has completed and flushed, then let the following kernel begin launching.  With
+// the launch attribute set (host::launch) a kernel's CTAs are dispatched, and run their prologue (barrier init,
+// TMEM allocation, tensor-map prefetch), while the previous kernel drains; without it both are no-ops.
+__device__ __forceinline__ void grid_dep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, int rows, int rows_per_group, int row_offset, long long group_stride,
                  __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  ptx::grid_dep_sync();
   constexpr int width = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 adapter_mix_kernel(float* __restrict__ x, const float* __restrict__ a, float w, int rows,
                    const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float eps,
                    __nv_bfloat16* __restrict__ ln_out) {
+  ptx::grid_dep_sync();
   constexpr int width = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_rows_kernel(const float* __restrict__ s, int ld, int col0, int rows, float* __restrict__ out_f32,
                    __nv_bfloat16* __restrict__ out_bf16, const float* __restrict__ anchors,
                    float* __restrict__ dots) {
+  ptx::grid_dep_sync();
   constexpr int width = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -162,6 +165,7 @@ l2norm_rows_kernel(const float* __restrict__ s, int ld, int col0, int rows, floa
 //                        partial sums are combined through smem in a fixed order (deterministic, no atomics).
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 row_inv_norm_kernel(const float* __restrict__ s, int ld, int col0, int rows, int width, float* __restrict__ inv) {
+  ptx::grid_dep_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -178,6 +182,7 @@ row_inv_norm_kernel(const float* __restrict__ s, int ld, int col0, int rows, int
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 det_mean_kernel(const float* __restrict__ s, int ld, int col0, int P, int width, const float* __restrict__ inv,
                 float* __restrict__ det) {
+  ptx::grid_dep_sync();
   __shared__ float4 part[WARPS_PER_BLOCK][32];
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,6 +216,7 @@ det_mean_kernel(const float* __restrict__ s, int ld, int col0, int P, int width,
 // image fp32 [B,3,S,S] -> A bf16 [B*G*G, Kpad]; k = c*ps*ps + i*ps + j (conv1.weight.view(width,-1) order)
 __global__ void im2col_kernel(const float* __restrict__ img, int B, int S, int ps, int G, int Kpad,
                               __nv_bfloat16* __restrict__ out) {
+  ptx::grid_dep_sync();
   const long long total = (long long)B * G * G * (Kpad / 2);
   const int K = 3 * ps * ps;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
@@ -235,11 +241,13 @@ __global__ void im2col_kernel(const float* __restrict__ img, int B, int S, int p
 
 __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int B, int L, int width) {
+  ptx::grid_dep_sync();
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < width; c += blockDim.x) x[(size_t)b * L * width + c] = cls[c] + pos[c];
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4) {
+  ptx::grid_dep_sync();
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4;
        t += (long long)gridDim.x * blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(x + t * 4);
@@ -270,10 +278,9 @@ int k::launch_layernorm(const float* x, const float* gamma, const float* beta, f
   if (rows <= 0) return host::OK;
   if (width % 128 != 0) return host::fail(host::ERR_INVALID, "layernorm: width %d must be a multiple of 128", width);
   if (rows_per_group <= 0) { rows_per_group = rows; row_offset = 0; group_stride = 0; }
-  DISPATCH_VEC(width, (layernorm_kernel<V><<<row_blocks(rows), WARPS_PER_BLOCK * 32, 0, stream>>>(
-                          x, gamma, beta, eps, rows, rows_per_group, row_offset, group_stride,
-                          static_cast<__nv_bfloat16*>(out_bf16), out_f32)));
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(layernorm_kernel<V>, dim3(row_blocks(rows)), dim3(WARPS_PER_BLOCK * 32),
+                                                     0, stream, x, gamma, beta, eps, rows, rows_per_group, row_offset,
+                                                     group_stride, static_cast<__nv_bfloat16*>(out_bf16), out_f32)));
   return host::OK;
 }
 
@@ -281,9 +288,9 @@ int k::launch_adapter_mix(float* x, const float* a, float w, int rows, int width
                           const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream) {
   if (rows <= 0) return host::OK;
   if (width % 128 != 0) return host::fail(host::ERR_INVALID, "adapter_mix: width %d must be a multiple of 128", width);
-  DISPATCH_VEC(width, (adapter_mix_kernel<V><<<row_blocks(rows), WARPS_PER_BLOCK * 32, 0, stream>>>(
-                          x, a, w, rows, ln_gamma, ln_beta, eps, static_cast<__nv_bfloat16*>(ln_out_bf16))));
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(adapter_mix_kernel<V>, dim3(row_blocks(rows)),
+                                                     dim3(WARPS_PER_BLOCK * 32), 0, stream, x, a, w, rows, ln_gamma, ln_beta,
+                                                     eps, static_cast<__nv_bfloat16*>(ln_out_bf16))));
   return host::OK;
 }
 
@@ -292,9 +299,9 @@ int k::launch_l2norm_rows(const float* s, int ld, int col0, int rows, int width,
   if (rows <= 0) return host::OK;
   if (width % 128 != 0 || ld % 4 != 0 || col0 % 4 != 0)
     return host::fail(host::ERR_INVALID, "l2norm: width %d / ld %d / col0 %d alignment", width, ld, col0);
-  DISPATCH_VEC(width, (l2norm_rows_kernel<V><<<row_blocks(rows), WARPS_PER_BLOCK * 32, 0, stream>>>(
-                          s, ld, col0, rows, out_f32, static_cast<__nv_bfloat16*>(out_bf16), anchors, dots)));
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(l2norm_rows_kernel<V>, dim3(row_blocks(rows)),
+                                                     dim3(WARPS_PER_BLOCK * 32), 0, stream, s, ld, col0, rows, out_f32,
+                                                     static_cast<__nv_bfloat16*>(out_bf16), anchors, dots)));
   return host::OK;
 }
 
@@ -303,11 +310,11 @@ int k::launch_det_mean(const float* s, int ld, int col0, int B, int P, int width
   if (B <= 0) return host::OK;
   if (width % 4 != 0 || ld % 4 != 0 || col0 % 4 != 0) return host::fail(host::ERR_INVALID, "det_mean: alignment");
   if (!inv_scratch) return host::fail(host::ERR_INVALID, "det_mean: scratch for %d row norms missing", B * P);
-  row_inv_norm_kernel<<<row_blocks(B * P), WARPS_PER_BLOCK * 32, 0, stream>>>(s, ld, col0, B * P, width, inv_scratch);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(row_inv_norm_kernel, dim3(row_blocks(B * P)), dim3(WARPS_PER_BLOCK * 32), 0, stream, s, ld,
+                                 col0, B * P, width, inv_scratch));
   dim3 grid(B, (width + 127) / 128);
-  det_mean_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, stream>>>(s, ld, col0, P, width, inv_scratch, det);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(det_mean_kernel, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, s, ld, col0, P, width,
+                                 (const float*)inv_scratch, det));
   return host::OK;
 }
 
@@ -317,14 +324,13 @@ int k::launch_im2col(const float* image, int B, int S, int ps, int Kpad, void* o
   const int G = S / ps;
   const long long total = (long long)B * G * G * (Kpad / 2);
   const int blocks = int(std::min<long long>((total + 255) / 256, 148LL * 32));
-  im2col_kernel<<<blocks, 256, 0, stream>>>(image, B, S, ps, G, Kpad, static_cast<__nv_bfloat16*>(out_bf16));
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(im2col_kernel, dim3(blocks), dim3(256), 0, stream, image, B, S, ps, G, Kpad,
+                                 static_cast<__nv_bfloat16*>(out_bf16)));
   return host::OK;
 }
 
 int k::launch_cls_rows(float* x, const float* cls, const float* pos, int B, int L, int width, cudaStream_t stream) {
-  cls_rows_kernel<<<B, 256, 0, stream>>>(x, cls, pos, B, L, width);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(cls_rows_kernel, dim3(B), dim3(256), 0, stream, x, cls, pos, B, L, width));
   return host::OK;
 }
 
@@ -332,8 +338,8 @@ int k::launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_
   if (n % 4 != 0) return host::fail(host::ERR_INVALID, "cast_bf16: n %% 4 != 0");
   const long long n4 = n / 4;
   const int blocks = int(std::min<long long>((n4 + 255) / 256, 148LL * 16));
-  cast_bf16_kernel<<<blocks, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out_bf16), n4);
-  AACLIP_CUDA_CHECK(cudaGetLastError());
+  AACLIP_CUDA_CHECK(host::launch(cast_bf16_kernel, dim3(blocks), dim3(256), 0, stream, x,
+                                 static_cast<__nv_bfloat16*>(out_bf16), n4));
   return host::OK;
 }
 

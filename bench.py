@@ -56,27 +56,68 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons / power every 50 ms while the timed region runs, through NVML in a thread of this
+    process (a child `nvidia-smi -lms` was seen to stall single steps by ~100 ms); falls back to nvidia-smi."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.h, self.stop_flag = index, [], None, None, False
         self.t0 = self.t1 = None   # the timed region, wall clock: only samples inside it are reported
+        self.sm_max, self.source = None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if bytes is str else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.source = "nvml"
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.h = None
+        try:
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                self.rows.append((time.time(), sm, self.sm_max, pw, {n for b, n in self.REASONS.items() if bits & b}))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+            c = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.time(), float(c[0]), float(c[1]), float(c[2]),
+                                  {n for n, v in zip(names, c[3:7]) if v.lower().startswith("active")}))
+            except (ValueError, IndexError):
+                pass
 
     def begin(self):
         self.t0 = time.time()
@@ -85,16 +126,17 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
-        self.rows = inside if inside else [r for _, r in self.rows[-3:]]
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        rows = inside if inside else self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
+        pw = sorted(r[3] for r in rows)
+        reasons = sorted(set().union(*[r[4] for r in rows])) if rows else []
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "power_w": pw[len(pw) // 2] if pw else None, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 def cpu_port_images_per_s(n_images: int, threads: int):
@@ -381,7 +423,8 @@ def main():
             "profiled_step": {"span_ms": span_ms, "sum_kernel_ms": tot_ms, "idle_between_kernels_ms": span_ms - tot_ms,
                               "note": "2 extra steps with CUDA events around every launch"}, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
-            "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)},
+            "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms),
+                        "all": [round(x, 3) for x in step_ms]},
         }
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
