@@ -22,6 +22,7 @@ constexpr int MAX_LEVELS = 8;
 struct SegPtrs { const void* p[MAX_LEVELS]; };
 
 // dots[l][row][c] = <seg_l[row, :], anchors[:, c]>   (row = b*P + p), c in {0,1}
+// General form (any E % 8 == 0, shared or per-image anchors): one warp per row, levels in turn.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 patch_dots_kernel(SegPtrs seg, int n_levels, const float* __restrict__ anchors, int anchors_batched, int rows, int P,
@@ -65,13 +66,57 @@ patch_dots_kernel(SegPtrs seg, int n_levels, const float* __restrict__ anchors, 
   }
 }
 
+// Streaming form for the A7 contract (bf16 tokens, E = 768, shared anchors): the lane's 24 anchor pairs live in
+// registers for the whole kernel, each warp walks rows with a grid stride and issues the 16-byte loads of ALL
+// levels of a row (up to 12 per lane) before it touches any of them, so enough bytes are in flight to run at HBM
+// speed (the general form above had 3).
+template <int NL>
+__global__ void __launch_bounds__(256)
+patch_dots_stream_kernel(SegPtrs seg, const float* __restrict__ anchors, int rows, float* __restrict__ dots) {
+  ptx::grid_dep_sync();
+  constexpr int E = 768, CH = E / 256;   // 3 chunks of 8 elements per lane
+  const int lane = threadIdx.x & 31;
+  float2 t[CH][8];                        // anchors of this lane's columns: (T[c][0], T[c][1])
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[i][j] = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
+  const int warps = gridDim.x * 8;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += warps) {
+    uint4 raw[NL][CH];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(seg.p[l]) + (size_t)row * E + lane * 8;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) raw[l][i] = __ldcs(reinterpret_cast<const uint4*>(f + i * 256));   // streamed once
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[l][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 v = __bfloat1622float2(h[j]);
+          d0 += v.x * t[i][2 * j].x + v.y * t[i][2 * j + 1].x;
+          d1 += v.x * t[i][2 * j].y + v.y * t[i][2 * j + 1].y;
+        }
+      }
+      d0 = ptx::warp_sum(d0);
+      d1 = ptx::warp_sum(d1);
+      if (lane == 0) *reinterpret_cast<float2*>(dots + ((size_t)l * rows + row) * 2) = make_float2(d0, d1);
+    }
+  }
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int G) {
   if (i < 0) i = -i;
   if (i >= G) i = 2 * (G - 1) - i;
   return i;
 }
 
-constexpr int BAND = 16;       // output rows per block
+constexpr int BAND = 48;       // output rows per block
 constexpr int HEAD_THREADS = 256;
 
 // mode: AACLIP_HEAD_*.  dots: [n_levels][B*G*G][2].
@@ -200,6 +245,141 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
   }
 }
 
+// ---- the A7 contract as ONE kernel (test modes, bf16 tokens, E = 768, shared anchors) -----------------------------
+// A thread-block cluster of 8 CTAs per image.  Phase 1: CTA r reads patches [r*P/8, (r+1)*P/8) of all levels
+// (every 16-byte load of a row issued before the first use; the lane's 24 anchor pairs stay in registers) and
+// leaves the level-summed scalars m in ITS shared memory.  After a cluster barrier every CTA gathers the whole
+// G x G map through distributed shared memory, blurs it, and writes 1/8 of the image's output rows with float4
+// stores; CTA 0 also produces the image score.  Bytes moved = the algorithmic 3.99 MB/image, once.
+constexpr int FUSED_CLUSTER = 8;
+constexpr int FUSED_THREADS = 128;
+template <int NL>
+__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS)
+head_fused_kernel(SegPtrs seg, const float* __restrict__ anchors, const float* __restrict__ det, int P, int G, int S,
+                  int mode, float* __restrict__ maps, float* __restrict__ scores) {
+  ptx::grid_dep_sync();
+  constexpr int E = 768, CH = E / 256;
+  extern __shared__ float sm[];
+  float* m_part = sm;                 // [chunk]   this CTA's patches
+  float* m = sm + 96;                 // [P]       whole map (gathered), chunk <= 96 keeps the offset fixed
+  float* t = m + P;                   // [P]       after the row blur
+  float* mb = t + P;                  // [P]       blurred map
+  __shared__ float wk[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int b = blockIdx.x / FUSED_CLUSTER;
+  const int chunk = (P + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  const int ksize = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 7 : 9;
+  const float sigma = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 1.0f : 1.5f;
+  if (tid == 0) {
+    float sum = 0.f;
+    for (int i = 0; i < ksize; ++i) {
+      const float x = float(i - ksize / 2);
+      wk[i] = expf(-(x * x) / (2.0f * sigma * sigma));
+      sum += wk[i];
+    }
+    for (int i = 0; i < ksize; ++i) wk[i] /= sum;
+  }
+  // ---- phase 1: anchor dots of this CTA's patches
+  float2 tt[CH][8];
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tt[i][j] = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
+  const int p_end = min(P, int(rank + 1) * chunk);
+  for (int p = int(rank) * chunk + warp; p < p_end; p += FUSED_THREADS / 32) {
+    const size_t row = (size_t)b * P + p;
+    uint4 raw[NL][CH];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(seg.p[l]) + row * E + lane * 8;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) raw[l][i] = __ldcs(reinterpret_cast<const uint4*>(f + i * 256));
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[l][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 v = __bfloat1622float2(h[j]);
+          d0 += v.x * tt[i][2 * j].x + v.y * tt[i][2 * j + 1].x;
+          d1 += v.x * tt[i][2 * j].y + v.y * tt[i][2 * j + 1].y;
+        }
+      }
+      d0 = ptx::warp_sum(d0);
+      d1 = ptx::warp_sum(d1);
+      acc += (100.0f * d1 + 1.0f - 100.0f * d0) * 0.5f;   // per level exactly as the reference (test.py:85)
+    }
+    if (lane == 0) m_part[p - int(rank) * chunk] = acc;
+  }
+  // image score (test.py:83-84) by one warp of the cluster's first CTA
+  if (rank == 0 && warp == 0 && scores != nullptr) {
+    float acc = 0.f;
+    for (int c = lane; c < E; c += 32) acc += det[(size_t)b * E + c] * __ldg(anchors + c * 2 + 1);
+    acc = ptx::warp_sum(acc);
+    if (lane == 0) scores[b] = (acc + 1.0f) * 0.5f;
+  }
+  ptx::cluster_sync();
+  // ---- gather the whole map through distributed shared memory
+  for (int i = tid; i < P; i += FUSED_THREADS) {
+    const uint32_t src_rank = uint32_t(i / chunk);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(m_part + (i - int(src_rank) * chunk))), "r"(src_rank));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    m[i] = v;
+  }
+  ptx::cluster_sync();   // nobody's m_part may disappear (CTA exit) before every peer has read it
+  // ---- blur along x, then along y (reflect padding: forward_utils.py:208-210)
+  const int half = ksize / 2;
+  for (int i = tid; i < P; i += FUSED_THREADS) {
+    const int gy = i / G, gx = i - gy * G;
+    float acc = 0.f;
+    for (int k = 0; k < ksize; ++k) acc += wk[k] * m[gy * G + reflect_idx(gx + k - half, G)];
+    t[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < P; i += FUSED_THREADS) {
+    const int gy = i / G, gx = i - gy * G;
+    float acc = 0.f;
+    for (int k = 0; k < ksize; ++k) acc += wk[k] * t[reflect_idx(gy + k - half, G) * G + gx];
+    mb[i] = acc;
+  }
+  __syncthreads();
+  // ---- bilinear, align_corners=True (forward_utils.py:211-213): this CTA's share of the output rows
+  const float scale = (S > 1) ? float(G - 1) / float(S - 1) : 0.f;
+  const int rows_per = (S + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  const int y0 = int(rank) * rows_per, ny = max(0, min(rows_per, S - y0));
+  const int xq = (S + 3) / 4;
+  for (int i = tid; i < ny * xq; i += FUSED_THREADS) {
+    const int yy = i / xq, x4 = (i - yy * xq) * 4;
+    const int y = y0 + yy;
+    const float sy = scale * float(y);
+    const int ry0 = min(int(sy), G - 1);
+    const int ry1 = ry0 + ((ry0 < G - 1) ? 1 : 0);
+    const float ly1 = sy - float(ry0), ly0 = 1.0f - ly1;
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int x = min(x4 + e, S - 1);
+      const float sx = scale * float(x);
+      const int rx0 = min(int(sx), G - 1);
+      const int rx1 = rx0 + ((rx0 < G - 1) ? 1 : 0);
+      const float lx1 = sx - float(rx0), lx0 = 1.0f - lx1;
+      const float top = lx0 * mb[ry0 * G + rx0] + lx1 * mb[ry0 * G + rx1];
+      const float bot = lx0 * mb[ry1 * G + rx0] + lx1 * mb[ry1 * G + rx1];
+      o[e] = ly0 * top + ly1 * bot;
+    }
+    float* dst = maps + ((size_t)b * S + y) * S + x4;
+    if (x4 + 3 < S && (S & 3) == 0) __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+    else for (int e = 0; e < 4 && x4 + e < S; ++e) dst[e] = o[e];
+  }
+}
+
 // scores[b] = (<det[b], anchors[:,1]> + 1) / 2      (test.py:83-84)
 __global__ void scores_kernel(const float* __restrict__ det, const float* __restrict__ anchors, int anchors_batched,
                               int B, int E, float* __restrict__ scores) {
@@ -261,6 +441,18 @@ int k::launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, 
   }
   const int rows = B * P;
   const int blocks = (rows + 7) / 8;
+  if (seg_is_bf16 && !anchors_batched && E == 768 && (n_levels == 4 || n_levels == 1)) {
+    // streaming form: each warp walks rows with a grid stride
+    int dev = 0;
+    AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
+    const int sms = host::sm_count(dev) > 0 ? host::sm_count(dev) : 148;
+    const int grid = std::min(blocks, sms * 2);   // 105 registers: two resident blocks per SM
+    if (n_levels == 4)
+      AACLIP_CUDA_CHECK(host::launch(patch_dots_stream_kernel<4>, dim3(grid), dim3(256), 0, stream, sp, anchors, rows, dots));
+    else
+      AACLIP_CUDA_CHECK(host::launch(patch_dots_stream_kernel<1>, dim3(grid), dim3(256), 0, stream, sp, anchors, rows, dots));
+    return host::OK;
+  }
   if (seg_is_bf16)
     AACLIP_CUDA_CHECK(host::launch(patch_dots_kernel<true>, dim3(blocks), dim3(256), 0, stream, sp, n_levels, anchors,
                                    anchors_batched, rows, P, E, dots));
@@ -308,6 +500,25 @@ extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg
   int G = 0;
   while ((G + 1) * (G + 1) <= P) ++G;  // H = int(sqrt(L)), forward_utils.py:201
   if (G * G != P) return host::fail(host::ERR_INVALID, "head: P=%d is not a square grid", P);
+  const bool test_mode = (mode == AACLIP_HEAD_TEST_INDUSTRIAL || mode == AACLIP_HEAD_TEST_MEDICAL);
+  const int pad = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 3 : 4;
+  if (maps_out != nullptr && test_mode && seg_is_bf16 && !anchors_batched && E == 768 && (n_levels == 4 || n_levels == 1) &&
+      (P + FUSED_CLUSTER - 1) / FUSED_CLUSTER <= 96 && G > pad && (scores_out == nullptr || det != nullptr)) {
+    // the whole head in one launch: cluster of 8 CTAs per image (head_fused_kernel)
+    SegPtrs sp;
+    for (int l = 0; l < n_levels; ++l) {
+      if (seg[l] == nullptr) return host::fail(host::ERR_INVALID, "head: seg[%d] is NULL", l);
+      sp.p[l] = seg[l];
+    }
+    const size_t smem = (96 + 3 * (size_t)P) * sizeof(float);
+    if (n_levels == 4)
+      AACLIP_CUDA_CHECK(host::launch(head_fused_kernel<4>, dim3(B * FUSED_CLUSTER), dim3(FUSED_THREADS), smem, stream, sp, anchors,
+                                     det, P, G, img_size, mode, maps_out, scores_out));
+    else
+      AACLIP_CUDA_CHECK(host::launch(head_fused_kernel<1>, dim3(B * FUSED_CLUSTER), dim3(FUSED_THREADS), smem, stream, sp, anchors,
+                                     det, P, G, img_size, mode, maps_out, scores_out));
+    return host::OK;
+  }
   if (maps_out != nullptr) {
     int dev = 0;
     AACLIP_CUDA_CHECK(cudaGetDevice(&dev));

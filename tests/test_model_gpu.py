@@ -267,3 +267,67 @@ def test_dropin_module_surface():
         a_o = orc.class_text_anchor(orc.encode_text(sd, ta, tn, layers=2, text_adapt_until=1),
                                     orc.encode_text(sd, ta, tabn, layers=2, text_adapt_until=1))
     assert anchor.shape == (768, 2) and (anchor.cpu() - a_o).abs().max().item() < 5e-3
+
+
+def test_full_batch64_properties_and_oracle_subset():
+    """BASELINE.json configs[1] at full size (B=64, ViT-L/14-336, one chunk): size-independent properties - every
+    image is an independent unit, so a permuted batch gives bit-identically permuted maps and scores - plus the
+    oracle on a 3-image subset (the CPU oracle needs ~0.3 s per image) with the north-star tolerances."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.VIT_L_14_336
+    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    eng = Engine(cfg, device=0, max_batch=64, text=False)
+    try:
+        eng.load_state_dicts(sd, ia, None)
+        img = synth.images(64, cfg, seed=77)
+        T = synth.anchors(cfg, seed=1)
+        maps, scores = eng.forward_fused(img.cuda(), T.cuda(), "Industrial")
+        perm = torch.randperm(64, generator=torch.Generator().manual_seed(5))
+        maps_p, scores_p = eng.forward_fused(img[perm].contiguous().cuda(), T.cuda(), "Industrial")
+        torch.cuda.synchronize()
+        assert torch.isfinite(maps).all() and torch.isfinite(scores).all()
+        assert torch.equal(maps_p.cpu(), maps.cpu()[perm]) and torch.equal(scores_p.cpu(), scores.cpu()[perm])
+        sub = [0, 31, 63]
+        with torch.no_grad():
+            seg_o, det_o = orc.visual_forward(sd, ia, img[sub])
+            map_o, score_o = orc.predict(seg_o, det_o, T, cfg.image_size, "Industrial")
+        m, s = maps.cpu()[sub], scores.cpu()[sub]
+        err = max((_mm(m[i]) - _mm(map_o[i])).abs().max().item() for i in range(len(sub)))
+        serr = (s - score_o).abs().max().item()
+        print(f"[B=64] normalised-map max-abs = {err:.3e}  score max-abs = {serr:.3e}")
+        assert err <= MAP_NORM_TOL and serr <= SCORE_TOL
+        assert torch.equal(torch.argsort(s), torch.argsort(score_o))
+    finally:
+        eng.close()
+
+
+def test_518px_operating_point_vs_oracle():
+    """the paper's 518-px setting - 37x37+1 = 1370 tokens, head 37x37 -> 518x518 - with a 3-layer
+    ViT-L-width model (L is a runtime parameter of every kernel; the full depth adds nothing new here)."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.ModelCfg(image_size=518, layers=3, t_layers=0, image_adapt_until=2, levels=[1, 2, 3])
+    assert cfg.tokens == 1370
+    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    eng = Engine(cfg, device=0, max_batch=2, text=False)
+    try:
+        eng.load_state_dicts(sd, ia, None)
+        img, T = synth.images(2, cfg, seed=9), synth.anchors(cfg, seed=1)
+        seg, det = eng.visual_forward(img.cuda())
+        maps, scores = eng.forward_fused(img.cuda(), T.cuda(), "Medical")
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            seg_o, det_o = orc.visual_forward(sd, ia, img, layers=3, image_adapt_until=2, levels=(1, 2, 3))
+            map_o, score_o = orc.predict(seg_o, det_o, T, cfg.image_size, "Medical")
+        e_seg = max((a.cpu() - b).abs().max().item() for a, b in zip(seg, seg_o))
+        e_det = (det.cpu() - det_o).abs().max().item()
+        e_map = max((_mm(maps.cpu()[i]) - _mm(map_o[i])).abs().max().item() for i in range(2))
+        e_sc = (scores.cpu() - score_o).abs().max().item()
+        print(f"[518px] seg {e_seg:.3e} det {e_det:.3e} normalised map {e_map:.3e} score {e_sc:.3e}")
+        assert maps.shape == (2, 518, 518)
+        assert e_seg <= SEG_TOL and e_det <= SEG_TOL and e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
+    finally:
+        eng.close()
