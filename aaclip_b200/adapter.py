@@ -164,3 +164,11 @@ class AdaptedCLIP(nn.Module):
         (anomaly maps [B,S,S] = sum over levels of calculate_similarity_map(test=True), image scores [B])."""
         eng = self._sync_engine(image.device)
         return eng.forward_fused(image.float().contiguous(), text_feature.float().contiguous(), domain)
+
+    @torch.no_grad()
+    def predict_stream(self, batches, text_feature: torch.Tensor, domain: str = "Industrial"):
+        """The batch loop of test.py:get_predictions (test.py:60-99) over an iterable of CPU image batches, pipelined
+        (upload of batch k+1 and download of batch k-1 overlap the compute of batch k).  Yields
+        (maps [B,S,S], scores [B]) as pinned CPU tensors, in order.  Batches must not exceed `max_batch`."""
+        eng = self._sync_engine(next(self.parameters()).device)
+        yield from eng.predict_stream(batches, text_feature, domain)

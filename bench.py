@@ -297,9 +297,14 @@ def main():
     value = total * args.steps / (ms / 1e3)
     finite = bool(torch.isfinite(maps).all() and torch.isfinite(scores).all())
 
-    # ---- per-kernel-class CUDA-event profile of the same step (2 extra steps, events around every launch)
+    # ---- per-kernel-class CUDA-event profile of the same step: events around every launch (aaclip_profile_*), run
+    #      right after the timed region on the same inputs; 3 settling steps are discarded (the idle time the events
+    #      insert lets the clocks rise a little above their steady state under the power cap), 3 are kept
     eng.profile(True)
-    prof_steps = 2
+    for i in range(3):
+        eng.forward_fused(inputs[i % n_rot], anchors, "Industrial")
+    eng.profile_read()
+    prof_steps = 3
     for i in range(prof_steps):
         eng.forward_fused(inputs[i % n_rot], anchors, "Industrial")
     prof = eng.profile_read()
@@ -322,7 +327,13 @@ def main():
         "frac": gemm_tflops / peaks["bf16_tflops_sustained"], "frac_of_burst_peak": gemm_tflops / peaks["bf16_tflops"],
         "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json); burst {peaks['bf16_tflops']}",
         "flop_per_launch_avg": gemm_flop_step / max(gemm_launches, 1), "launches_per_step": gemm_launches,
-        "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / tot_ms, "traffic": None,
+        "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / tot_ms,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of the two
+        # largest GEMMs (profiles/r1_ncu_gemm_full.txt): c_fc 331 MB (algorithmic 386 MB: part of the 302 MB bf16
+        # output is still in L2 when the kernel ends), c_proj 596 MB (algorithmic 613 MB incl. the fp32 residual RMW)
+        "traffic": (330.9e6 + 596.4e6) / 2, "traffic_detail": {"gemm_fc": 330.9e6, "gemm_proj": 596.4e6,
+                                                                "algorithmic": {"gemm_fc": 386.4e6, "gemm_proj": 613.3e6}},
+        "achieved_in_timed_region_estimate": gemm_tflops * (span_ms / (ms / args.steps)),
         "whole_step_tflops": F_IMG * B / (ms / args.steps / 1e3) / 1e12,
         "whole_step_frac": F_IMG * B / (ms / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
     }
@@ -421,7 +432,7 @@ def main():
                        "outputs_finite": finite},
             "roofline": roofline, "roofline_head": head, "kernels": kern,
             "profiled_step": {"span_ms": span_ms, "sum_kernel_ms": tot_ms, "idle_between_kernels_ms": span_ms - tot_ms,
-                              "note": "2 extra steps with CUDA events around every launch"}, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                              "note": "3 extra steps (after 3 discarded) with CUDA events around every launch"}, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms),
                         "all": [round(x, 3) for x in step_ms]},

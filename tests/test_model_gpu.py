@@ -260,6 +260,14 @@ def test_dropin_module_surface():
         seg_o2, _ = orc.visual_forward(sd, ia2, img, layers=4, image_adapt_until=2, levels=(1, 2, 3, 4))
     assert max((a.cpu() - b).abs().max().item() for a, b in zip(pf2, seg_o2)) < SEG_TOL
     assert (pf2[0] - patch_features[0]).abs().max().item() > 1e-2
+    # fused per-batch and pipelined-loop forms agree with the per-level form (same kernels up to the head entry)
+    with torch.no_grad():
+        m_f, s_f = model.predict(img.cuda(), T.cuda(), "Industrial")
+        streamed = list(model.predict_stream([img[:2], img[2:]], T, "Industrial"))
+    assert (m_f.cpu() - maps.cpu()).abs().max().item() < 1e-3
+    assert torch.equal(torch.cat([m for m, _ in streamed]), m_f.cpu())
+    assert torch.equal(torch.cat([sc for _, sc in streamed]), s_f.cpu())
+    assert (s_f.cpu() - (pred[:, 1].cpu() + 1) / 2).abs().max().item() < 1e-5
     # text anchors from token ids
     tn, tabn = synth.tokens(6, cfg, seed=7), synth.tokens(10, cfg, seed=8)
     anchor = class_text_embedding(model, tn.cuda(), tabn.cuda())
