@@ -144,16 +144,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int w = first; w < n_items; w += stride, ++n) {
         const Item it = decode_item(w, n_qt, heads, L, causal);
         const uint32_t qb = n % NQ, qph = (n / NQ) & 1u;
-        ptx::mbar_wait(&bars->q_empty[qb], qph ^ 1u);
+        ptx::mbar_wait_spin(&bars->q_empty[qb], qph ^ 1u);
         ptx::mbar_arrive_expect_tx(&bars->q_full[qb], Q_BYTES);
         ptx::tma_load_2d(smem + LY::OFF_Q + qb * Q_BYTES, &tmQ, &bars->q_full[qb], it.h * D, it.row_base + it.q0);
         for (int j = 0; j < it.n_kv; ++j) {
-          ptx::mbar_wait(&bars->k_empty[kst], kph ^ 1u);
+          ptx::mbar_wait_spin(&bars->k_empty[kst], kph ^ 1u);
           ptx::mbar_arrive_expect_tx(&bars->k_full[kst], KV_BYTES);
           ptx::tma_load_2d(smem + LY::OFF_K + kst * KV_BYTES, &tmKV, &bars->k_full[kst], W + it.h * D,
                            it.row_base + j * BKV);
           if (++kst == NSTK) { kst = 0; kph ^= 1u; }
-          ptx::mbar_wait(&bars->v_empty[vst], vph ^ 1u);
+          ptx::mbar_wait_spin(&bars->v_empty[vst], vph ^ 1u);
           ptx::mbar_arrive_expect_tx(&bars->v_full[vst], KV_BYTES);
           ptx::tma_load_2d(smem + LY::OFF_V + vst * KV_BYTES, &tmKV, &bars->v_full[vst], 2 * W + it.h * D,
                            it.row_base + j * BKV);
@@ -180,8 +180,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       auto issue_s = [&]() {   // S tile s_g -> TMEM S[s_g & 1]
         if (s_w >= n_items) return;
         const uint32_t qb = s_n % NQ;
-        if (s_j == 0) ptx::mbar_wait(&bars->q_full[qb], (s_n / NQ) & 1u);
-        ptx::mbar_wait(&bars->k_full[s_st], s_ph);
+        if (s_j == 0) ptx::mbar_wait_spin(&bars->q_full[qb], (s_n / NQ) & 1u);
+        ptx::mbar_wait_spin(&bars->k_full[s_st], s_ph);
         ptx::tc_fence_after();
         const uint32_t qd = q_lo + qb * (Q_BYTES >> 4);
         const uint32_t kb = k_lo + uint32_t(s_st) * (KV_BYTES >> 4);
@@ -208,9 +208,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const Item it = decode_item(w, n_qt, heads, L, causal);
         for (int j = 0; j < it.n_kv; ++j, ++g) {
           if (n == 1) TRACE(16, j);
-          ptx::mbar_wait(&bars->p_full[g & 1u], (g >> 1) & 1u);  // P_g in smem, S[g&1] drained, O rescaled / drained
+          ptx::mbar_wait_spin(&bars->p_full[g & 1u], (g >> 1) & 1u);  // P_g in smem, S[g&1] drained, O rescaled / drained
           if (n == 1) TRACE(17, j);
-          ptx::mbar_wait(&bars->v_full[st], ph);
+          ptx::mbar_wait_spin(&bars->v_full[st], ph);
           ptx::tc_fence_after();
           if (n == 1) TRACE(18, j);
           // A: P tile g = key columns [(g&1)*32, +32) of the 128-B swizzled P rows: +64 B per tile, +32 B per 16 keys
@@ -218,9 +218,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t pb = p_lo + (g & 1u) * 4u;
           const uint32_t vb = v_lo + uint32_t(st) * (KV_BYTES >> 4);
           const uint32_t acc0 = j > 0 ? 1u : 0u;   // O accumulates over the key tiles of one item
-          const int ksteps = min(BKV / 16, (it.kv_end - j * BKV + 15) >> 4);   // ragged last tile: skip hidden keys
-          for (int k = 0; k < ksteps; ++k)
-            ptx::mma_f16_ss<1>(t_o, desc(pb + k * 2), desc(vb + k * 128), idesc_o, k != 0 ? 1u : acc0);
+          if (it.kv_end - j * BKV > 16) {
+            ptx::mma_f16_ss<1>(t_o, desc(pb), desc(vb), idesc_o, acc0);
+            ptx::mma_f16_ss<1>(t_o, desc(pb + 2), desc(vb + 128), idesc_o, 1u);
+          } else {   // ragged last tile: the second 16-key step is fully hidden
+            ptx::mma_f16_ss<1>(t_o, desc(pb), desc(vb), idesc_o, acc0);
+          }
           ptx::mma_commit(&bars->v_empty[st]);
           ptx::mma_commit(&bars->p_free[g & 1u]);   // PV_g has landed in O and has finished reading P half g & 1
           if (++st == NSTV) { st = 0; ph ^= 1u; }
