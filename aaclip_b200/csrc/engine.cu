@@ -122,7 +122,8 @@ struct aaclip_ctx {
   bf16* t_final = nullptr;
   // workspaces
   int cap_rows = 0;  // rows of the token-major buffers
-  float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr, *rownorm = nullptr;
+  float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr, *rownorm = nullptr,
+        *partials = nullptr;   // [levels][B*P][E/128] float4 partial sums of the fused seg_proj epilogue
   bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *col = nullptr, *tap = nullptr;
   // host-buffer pipeline (aaclip_submit_host / aaclip_wait_host): two slots of device staging, copy-in, compute
   // and copy-out streams, so the H2D of batch k+1 and the D2H of batch k-1 overlap the compute of batch k
@@ -251,16 +252,28 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
                               nullptr, st));
       const bool want_det = last && (det_out != nullptr);
       const int n_out = want_det ? 2 * E : E;
-      RUN(PC_GEMM_SEGDET, k::launch_gemm(c->tap, w, c->segdet_w[level], w, prow, n_out, w, nullptr, c->s, 2 * E,
-                         cfg.proj_relu ? gemm::ACT_LEAKY : gemm::ACT_NONE, gemm::OUT_F32, nullptr, 0, cg, st));
       float* so = (seg_out && seg_out[level]) ? seg_out[level] + seg_off : nullptr;
-      float* dl = dots ? dots + (size_t)level * prow * 2 : nullptr;
-      if (so || dl) {
-        RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
+      const int act = cfg.proj_relu ? gemm::ACT_LEAKY : gemm::ACT_NONE;
+      if (dots && !so && E % 128 == 0) {
+        // fused path: the normalised seg tokens are never materialised - the GEMM epilogue leaves the partial sums
+        // of ||f||^2, <f,T0>, <f,T1> per 128-column slice (det_proj columns on the last level are still stored)
+        RUN(PC_GEMM_SEGDET, k::launch_gemm(c->tap, w, c->segdet_w[level], w, prow, n_out, w, nullptr, c->s, 2 * E, act,
+                           gemm::OUT_DOTS, nullptr, 0, cg, st, anchors,
+                           c->partials + (size_t)level * prow * (E / 128) * 4, E));
+      } else {
+        RUN(PC_GEMM_SEGDET, k::launch_gemm(c->tap, w, c->segdet_w[level], w, prow, n_out, w, nullptr, c->s, 2 * E, act,
+                           gemm::OUT_F32, nullptr, 0, cg, st));
+        float* dl = dots ? dots + (size_t)level * prow * 2 : nullptr;
+        if (so || dl) {
+          RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
+        }
       }
       if (want_det) { RUN(PC_DET_MEAN, k::launch_det_mean(c->s, 2 * E, E, B, P, E, c->rownorm, det_out, st)); c->launches++; }
       ++level;
     }
+  }
+  if (dots && !seg_out && E % 128 == 0) {
+    RUN(PC_L2NORM, k::launch_dots_finish(c->partials, cfg.n_levels, prow, E / 128, dots, st));
   }
   return host::OK;
 }
@@ -344,6 +357,7 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
   A(c->alloc(&c->qkv, rows * 3 * max_w)); A(c->alloc(&c->att, rows * max_w)); A(c->alloc(&c->h, rows * max_ff));
   A(c->alloc(&c->col, prow * c->Kpad)); A(c->alloc(&c->tap, prow * w)); A(c->alloc(&c->s, prow * 2 * E));
   A(c->alloc(&c->dots, (long long)cfg->n_levels * prow * 2)); A(c->alloc(&c->det, (long long)cfg->max_batch * E)); A(c->alloc(&c->rownorm, prow));
+  A(c->alloc(&c->partials, (long long)cfg->n_levels * prow * ((E + 127) / 128) * 4));
   if (rc != host::OK) { aaclip_destroy(c); return rc; }
   *out = c;
   return host::OK;

@@ -28,7 +28,7 @@
 namespace gemm {
 
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_QUICK_GELU = 2, ACT_LEAKY = 3 };
-enum Out : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_RESID = 2, OUT_F32_PATCH = 3 };
+enum Out : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_RESID = 2, OUT_F32_PATCH = 3, OUT_DOTS = 4 };
 
 struct Args {
   int M, N, K;
@@ -37,6 +37,12 @@ struct Args {
   int ldo;
   const float* pos;   // OUT_F32_PATCH: positional embedding [P+1, N]
   int P;              // OUT_F32_PATCH: patches per image
+  // OUT_DOTS (seg_proj + F.normalize + anchor similarity, model/adapter.py:106-109 + forward_utils.py:199):
+  // columns [0, dots_cols) are never stored; each 128-column slice of a row leaves (sum of squares, <row, T[:,0]>,
+  // <row, T[:,1]>) in partials[row][slice]; columns >= dots_cols (det_proj on the last level) are stored as fp32.
+  const float* anchors;   // [dots_cols, 2]
+  float4* partials;       // [M][dots_cols / 128]
+  int dots_cols;          // multiple of 128
 };
 
 template <int CG>
@@ -215,6 +221,33 @@ __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage,
   }
 }
 
+// OUT_DOTS epilogue of one warp: 32 rows x 128 accumulator columns -> three partial sums per row (lane == row).
+template <int ACT, typename ArriveFn>
+__device__ __forceinline__ void epilogue_dots(uint32_t t_addr, int row0, int col0, uint32_t lane, const Args& a,
+                                              ArriveFn&& release_tmem) {
+  float ss = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
+    ptx::tmem_ld_wait();
+    if (c == 3) release_tmem();
+    const int col = col0 + c * 32;
+    float f[32];
+    bias_act32<ACT>(v, f, a.bias, col);
+    const float4* t4 = reinterpret_cast<const float4*>(a.anchors + size_t(col) * 2);   // same address in every lane
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 t = __ldg(t4 + j);   // T[col+2j][0..1], T[col+2j+1][0..1]
+      ss = fmaf(f[2 * j], f[2 * j], fmaf(f[2 * j + 1], f[2 * j + 1], ss));
+      d0 = fmaf(f[2 * j], t.x, fmaf(f[2 * j + 1], t.z, d0));
+      d1 = fmaf(f[2 * j], t.y, fmaf(f[2 * j + 1], t.w, d1));
+    }
+  }
+  const int row = row0 + int(lane);
+  if (row < a.M) a.partials[size_t(row) * (a.dots_cols >> 7) + (col0 >> 7)] = make_float4(ss, d0, d1, 0.f);
+}
+
 template <int CG, int ACT, int OUT>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -357,6 +390,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (c == 3) release_tmem();
           epilogue_chunk<ACT, OUT>(v, row0 + int(lane), n_blk * C::BN + int(half) * 128 + c * 32, args);
         }
+      } else if constexpr (OUT == OUT_DOTS) {
+        const int col0 = n_blk * C::BN + int(half) * 128;
+        if (col0 < args.dots_cols) epilogue_dots<ACT>(t_addr, row0, col0, lane, args, release_tmem);
+        else epilogue_staged<ACT, OUT_F32>(t_addr, stage, &tmC, row0, col0, lane, args, release_tmem);
       } else {
         epilogue_staged<ACT, OUT>(t_addr, stage, &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args,
                                   release_tmem);

@@ -8,8 +8,14 @@ namespace k {
 
 // out = epilogue(A[M,K] . W[N,K]^T); A, W bf16 K-contiguous (pitches lda/ldw elements, multiples of 8).
 // act: gemm::Act, out_mode: gemm::Out, cta_group: 1 or 2.
+// out_mode OUT_DOTS: see gemm::Args (anchors [dots_cols,2], partials float4 [M][dots_cols/128]).
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out,
-                int ldo, int act, int out_mode, const float* pos, int P, int cta_group, cudaStream_t stream);
+                int ldo, int act, int out_mode, const float* pos, int P, int cta_group, cudaStream_t stream,
+                const float* anchors = nullptr, void* partials = nullptr, int dots_cols = 0);
+
+// dots[l][r] = (d0, d1) / max(sqrt(ss), 1e-12) summed over the n_slices 128-column partials of row r, level l
+// partials: [n_levels][rows][n_slices] float4 (ss, d0, d1, -)
+int launch_dots_finish(const void* partials, int n_levels, int rows, int n_slices, float* dots, cudaStream_t stream);
 
 // LayerNorm over the last dim (width % 128 == 0, <= 4096), fp32 in, affine, eps; one warp per row.
 //   rows are read at  x + (r / rows_per_group) * group_stride + (r % rows_per_group + row_offset) * width

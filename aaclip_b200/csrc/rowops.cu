@@ -18,10 +18,12 @@ constexpr int WARPS_PER_BLOCK = 8;
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // Row of VEC*128 floats held as VEC float4 per lane: element index = (i*32 + lane)*4 + {0..3}.
+// The rows (the fp32 residual stream, 151 MB at B=64) are read once per kernel and are larger than L2: stream them
+// (evict-first) so that they do not push out the bf16 output the next GEMM is about to read.
 template <int VEC>
 __device__ __forceinline__ void load_row(const float* row, int lane, float4 (&v)[VEC]) {
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) v[i] = *reinterpret_cast<const float4*>(row + (i * 32 + lane) * 4);
+  for (int i = 0; i < VEC; ++i) v[i] = __ldcs(reinterpret_cast<const float4*>(row + (i * 32 + lane) * 4));
 }
 template <int VEC>
 __device__ __forceinline__ float row_sum(const float4 (&v)[VEC]) {
@@ -213,6 +215,21 @@ det_mean_kernel(const float* __restrict__ s, int ld, int col0, int P, int width,
   }
 }
 
+// dots[l][r] = (sum d0, sum d1) / max(sqrt(sum ss), 1e-12) over the 128-column partials the seg_proj GEMM epilogue left
+__global__ void __launch_bounds__(256)
+dots_finish_kernel(const float4* __restrict__ partials, long long total_rows, int n_slices, float2* __restrict__ dots) {
+  ptx::grid_dep_sync();
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= total_rows) return;
+  float ss = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int i = 0; i < n_slices; ++i) {
+    const float4 p = partials[r * n_slices + i];
+    ss += p.x; d0 += p.y; d1 += p.z;
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  dots[r] = make_float2(d0 * inv, d1 * inv);
+}
+
 // image fp32 [B,3,S,S] -> A bf16 [B*G*G, Kpad]; k = c*ps*ps + i*ps + j (conv1.weight.view(width,-1) order)
 __global__ void im2col_kernel(const float* __restrict__ img, int B, int S, int ps, int G, int Kpad,
                               __nv_bfloat16* __restrict__ out) {
@@ -315,6 +332,14 @@ int k::launch_det_mean(const float* s, int ld, int col0, int B, int P, int width
   dim3 grid(B, (width + 127) / 128);
   AACLIP_CUDA_CHECK(host::launch(det_mean_kernel, grid, dim3(WARPS_PER_BLOCK * 32), 0, stream, s, ld, col0, P, width,
                                  (const float*)inv_scratch, det));
+  return host::OK;
+}
+
+int k::launch_dots_finish(const void* partials, int n_levels, int rows, int n_slices, float* dots, cudaStream_t stream) {
+  const long long total = (long long)n_levels * rows;
+  if (total <= 0) return host::OK;
+  AACLIP_CUDA_CHECK(host::launch(dots_finish_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream,
+                                 static_cast<const float4*>(partials), total, n_slices, reinterpret_cast<float2*>(dots)));
   return host::OK;
 }
 
