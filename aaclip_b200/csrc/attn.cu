@@ -240,7 +240,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16);
     const uint32_t t_o = t_lane + 2u * BKV;
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    const float RESCALE_LOG2 = rescale_log2;       // lazy rescale: tolerate p up to 2^8 before touching O
+    const float RESCALE_MAX = exp2f(rescale_log2); // lazy rescale: tolerate p (and tile row sums) up to 2^8 before touching O
     uint8_t* p_row = smem + LY::OFF_P + row * 128;
     uint8_t* p_warp = smem + LY::OFF_P + quarter * 32u * 128u;   // this warp's 32 rows x 128 B (output staging)
     const uint32_t sw = uint32_t(row & 7);
@@ -260,33 +260,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (i >= limit) sv[i] = 0xff800000u;
     };
     // One streaming pass over NG 8-key groups of the tile: p = exp2((s - m) * c) -> bf16 -> swizzled smem (16 B per
-    // group, stored as soon as packed), fp32 row sum and the tile's row max, all in one branch-free instruction
-    // stream so that the FMNMX / FADD / F2FP / STS work hides under the SFU (MUFU.EX2) latency.
+    // group, stored as soon as packed) and the fp32 row sum, in one branch-free instruction stream so that the
+    // FFMA2 / FADD2 / F2FP / STS work hides under the SFU (MUFU.EX2) latency.  No row max here: the row sum bounds
+    // every p of the tile, which is all the stale-stabiliser check needs.
     // `half` selects the tile's 64-B half of the 128-B P row (chunks half*4 .. half*4+3).
-    auto exp_pass = [&](auto ng_tag, uint32_t half, float mc, float& rowsum, float& rowmax) {
+    auto exp_pass = [&](auto ng_tag, uint32_t half, float mc, float& rowsum) {
       constexpr int NG = decltype(ng_tag)::value;
-      float rs2[2] = {0.f, 0.f};
-      float mx2[2] = {-INFINITY, -INFINITY};
+      float r0 = 0.f, r1 = 0.f;
+      const float nmc = -mc;
 #pragma unroll
       for (int g8 = 0; g8 < NG; ++g8) {
-        float e[8];
+        float x[8], e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float x = fmaf(__uint_as_float(sv[8 * g8 + i]), c, -mc);
-          e[i] = (i >= 8 - POLY) ? ptx::ex2_poly3(x) : ptx::ex2_approx(x);
-        }
-        mx2[0] = fmaxf(mx2[0], fmaxf(fmaxf(__uint_as_float(sv[8 * g8 + 0]), __uint_as_float(sv[8 * g8 + 1])),
-                                     fmaxf(__uint_as_float(sv[8 * g8 + 2]), __uint_as_float(sv[8 * g8 + 3]))));
-        mx2[1] = fmaxf(mx2[1], fmaxf(fmaxf(__uint_as_float(sv[8 * g8 + 4]), __uint_as_float(sv[8 * g8 + 5])),
-                                     fmaxf(__uint_as_float(sv[8 * g8 + 6]), __uint_as_float(sv[8 * g8 + 7]))));
-        rs2[g8 & 1] += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+        for (int i = 0; i < 8; i += 2)
+          ptx::ffma2(x[i], x[i + 1], __uint_as_float(sv[8 * g8 + i]), __uint_as_float(sv[8 * g8 + i + 1]), c, nmc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = (i >= 8 - POLY) ? ptx::ex2_poly3(x[i]) : ptx::ex2_approx(x[i]);
+        float a0, a1, b0, b1;
+        ptx::fadd2(a0, a1, e[0], e[1], e[2], e[3]);
+        ptx::fadd2(b0, b1, e[4], e[5], e[6], e[7]);
+        ptx::fadd2(a0, a1, a0, a1, b0, b1);
+        ptx::fadd2(r0, r1, r0, r1, a0, a1);
         const uint32_t a = half ? p_addr[4 + g8] : p_addr[g8];
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ptx::pack_bf16x2(e[0], e[1])),
                      "r"(ptx::pack_bf16x2(e[2], e[3])), "r"(ptx::pack_bf16x2(e[4], e[5])),
                      "r"(ptx::pack_bf16x2(e[6], e[7])) : "memory");
       }
-      rowsum = rs2[0] + rs2[1];
-      rowmax = fmaxf(mx2[0], mx2[1]);
+      rowsum = r0 + r1;
+    };
+    // row max over the first NG 8-key groups of the tile in registers
+    auto tile_max = [&](bool four) {
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < BKV; i += 2)
+        if (i < 16 || four)
+          mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+      return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     };
     using NG4 = std::integral_constant<int, 4>;
     using NG2 = std::integral_constant<int, 2>;
@@ -325,12 +334,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           four = (it.kv_end - kv0) > 16;
           if ((kv0 + BKV > L) || (causal && kv0 + BKV > it.q0 + 1)) mask_scores(kv0, it.q0, qi);
           if (j == 0) {   // adopt the true row max (a fully hidden row - rows >= L, never stored - uses 0)
-            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-            for (int i = 0; i < BKV; i += 2)
-              if (i < 16 || four)
-                mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
-            const float mt0 = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            const float mt0 = tile_max(four);
             m_used = (mt0 == -INFINITY) ? 0.f : mt0;
             if (store_pending) {   // the previous item's output store must have finished reading these P rows
               if (lane == 0) ptx::bulk_wait_read<0>();
@@ -340,15 +344,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
         TRS(1);
-        float rs, mt;
-        if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs, mt);
-        else exp_pass(NG2{}, half, m_used * c, rs, mt);
+        float rs;
+        if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs);
+        else exp_pass(NG2{}, half, m_used * c, rs);
         TRS(2);
-        // ---- stale stabiliser check: only when some row's max grew by more than 2^RESCALE is O touched
-        const bool grow = (mt - m_used) * c > RESCALE_LOG2;
-        if (__any_sync(0xffffffffu, grow)) {          // warp-uniform: tcgen05.ld/st are warp-collective
-          const float m_next = grow ? mt : m_used;
-          const float alpha = ptx::ex2_approx((m_used - m_next) * c);   // 1 for rows that keep their max
+        // ---- stale stabiliser check: p <= row sum, so a row sum within 2^RESCALE proves every p of the tile is; only
+        //      when some row exceeds it (its max has grown a lot since the stabiliser was adopted) is O touched
+        if (__any_sync(0xffffffffu, !(rs <= RESCALE_MAX))) {   // warp-uniform: tcgen05.ld/st are warp-collective
+          // S_g is still in TMEM (released by the p_full arrive): reload it, find the true tile max of the rows that
+          // tripped the check and restabilise them; every other row keeps its stabiliser (alpha = 1)
+          const bool trip = !(rs <= RESCALE_MAX);
+          load_scores(g);
+          ptx::tmem_ld_wait();
+          const bool masked = !FAST && ((kv0 + BKV > L) || (causal && kv0 + BKV > it.q0 + 1));
+          if (masked) mask_scores(kv0, it.q0, qi);
+          const float mt = tile_max(FAST || four);
+          const float m_next = trip ? fmaxf(m_used, mt) : m_used;
+          const float alpha = ptx::ex2_approx((m_used - m_next) * c);
           if (j > 0) {
             // PV_{g-1} must have landed in O.  p_free[b] completes with PV_b, PV_{b+2}, ...; S_g complete implies
             // PV_{g-3} complete (issue order) and PV_{g+1} needs this warp's P_{g+1}: the barrier is in the phase
@@ -365,15 +377,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               ptx::tmem_st_32x32b_x32(t_o + hh * 32, v);
             }
             ptx::tmem_st_wait();
+            // the O loads above overwrote nothing of sv, but the tile is redone from a fresh copy for simplicity
+            load_scores(g);
+            ptx::tmem_ld_wait();
+            if (masked) mask_scores(kv0, it.q0, qi);
           }
           l *= alpha;
           m_used = m_next;
-          // redo the tile against the new stabiliser (S_g is still in TMEM: it is released by the p_full arrive)
-          load_scores(g);
-          ptx::tmem_ld_wait();
-          if (!FAST && ((kv0 + BKV > L) || (causal && kv0 + BKV > it.q0 + 1))) mask_scores(kv0, it.q0, qi);
-          if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs, mt);
-          else exp_pass(NG2{}, half, m_used * c, rs, mt);
+          if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs);
+          else exp_pass(NG2{}, half, m_used * c, rs);
         }
         l += rs;
         TRS(3);

@@ -296,6 +296,22 @@ __device__ __forceinline__ float ex2_poly3(float x) {
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2, one issue slot for two lanes of work)
+__device__ __forceinline__ void ffma2(float& o0, float& o1, float a0, float a1, float b, float c) {
+  uint64_t a, bb, cc, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(d));
+}
+__device__ __forceinline__ void fadd2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  uint64_t a, b, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(d));
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
