@@ -402,9 +402,9 @@ def main():
         torch.cuda.synchronize()
         hms = h0.elapsed_time(h1) / reps
         gbs = HEAD_BYTES_IMG * B / (hms / 1e3) / 1e9
-        head = {"bound": "hbm", "kernel": "patch_dots + head_maps + scores (aaclip_anomaly_head)", "achieved": gbs,
+        head = {"bound": "hbm", "kernel": "head_fused_kernel (aaclip_anomaly_head: cluster of 8 CTAs per image, dots -> DSMEM gather -> blur -> bilinear -> map + score)", "achieved": gbs,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "ms": hms,
-                "images_per_s": B / (hms / 1e3), "note": "inputs 113 MB < L2: back-to-back repeats are L2-assisted"}
+                "images_per_s": B / (hms / 1e3), "note": "4 levels x 56.6 MB of bf16 tokens = 226 MB per call > 126 MB L2: repeats stream from HBM"}
     except Exception as e:  # the head microbench must never sink the headline line
         head = {"error": str(e)}
 
