@@ -66,6 +66,8 @@ class ClockSampler:
         self.sm_max, self.source = None, None
 
     def start(self):
+        if os.environ.get("AACLIP_BENCH_NO_SAMPLER"):   # diagnostics: does the sampler perturb the timed region?
+            return
         try:
             import pynvml
             import torch

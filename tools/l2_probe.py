@@ -40,3 +40,16 @@ def six_halves():   # same work: 6 layers on each half, half by half (x of one h
     for _ in range(6): layer(h2)
 print(f"6 layers, B=64 in one go : {timeit(six_full):8.3f} ms")
 print(f"6 layers, 2 x B=32       : {timeit(six_halves):8.3f} ms")
+# the same under the sustained power cap (2.5 s each)
+import time
+def sustained(fn, secs=2.5):
+    t0 = time.perf_counter(); marks = []
+    while time.perf_counter() - t0 < secs:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4): fn()
+        e1.record(); e1.synchronize()
+        marks.append((time.perf_counter() - t0, e0.elapsed_time(e1) / 4))
+    late = [ms for t, ms in marks if t > secs / 2]
+    return sum(late) / len(late)
+print(f"sustained: B=64 in one go {sustained(six_full):8.3f} ms   2 x B=32 {sustained(six_halves):8.3f} ms")
