@@ -101,3 +101,43 @@ def create_model(model_name: str = "ViT-L-14-336", img_size: int = 336, pretrain
         raise RuntimeError("pretrained weights are not available offline; load a state_dict instead")
     cfg = ModelCfg(image_size=img_size)
     return CLIP(cfg, text=text)
+
+
+def resize_pos_embed(state_dict, grid_size: int, interpolation: str = "bicubic", antialias: bool = True) -> bool:
+    """Load-time rescale of `visual.positional_embedding` when a checkpoint trained at one resolution is used at
+    another (the paper's 518-px setting from the 336-px OpenAI weights).  Semantics of model/model.py:395-426: the
+    class-token row is kept, the patch grid is resampled with F.interpolate(bicubic, antialias=True,
+    align_corners=False).  Mutates `state_dict`; returns True if a resize happened.  Host-side load-time plumbing."""
+    import math
+
+    import torch.nn.functional as F
+    old = state_dict.get("visual.positional_embedding", None)
+    if old is None:
+        return False
+    new_len = grid_size * grid_size + 1
+    if new_len == old.shape[0]:
+        return False
+    tok, img = old[:1], old[1:]
+    g0 = int(math.sqrt(img.shape[0]))
+    if g0 * g0 != img.shape[0]:
+        raise ValueError(f"positional embedding of {old.shape[0]} rows is not 1 + a square grid")
+    img = img.reshape(1, g0, g0, -1).permute(0, 3, 1, 2)
+    img = F.interpolate(img.float(), size=(grid_size, grid_size), mode=interpolation, antialias=antialias,
+                        align_corners=False)
+    img = img.permute(0, 2, 3, 1).reshape(grid_size * grid_size, -1).to(old.dtype)
+    state_dict["visual.positional_embedding"] = torch.cat([tok, img], dim=0)
+    return True
+
+
+def load_checkpoint(model: CLIP, state_dict, strict: bool = True):
+    """model/clip.py:60-82 (load_checkpoint) for the container: drops the keys the reference drops, rescales the
+    positional embedding to the model's grid, then load_state_dict.  `state_dict` may be an OpenAI / open_clip
+    ViT-L/14 state dict (model/openai.py:17-83 converts to the same keys) or ours."""
+    sd = dict(state_dict)
+    for k in ("input_resolution", "context_length", "vocab_size"):
+        sd.pop(k, None)
+    resize_pos_embed(sd, model.visual.grid_size[0])
+    own = model.state_dict()
+    if not strict:
+        sd = {k: v for k, v in sd.items() if k in own}
+    return model.load_state_dict(sd, strict=strict)

@@ -167,6 +167,25 @@ def main():
                 "class_names_mvtec": list(CLASS_NAMES["MVTec"])},
                os.path.join(out_dir, "text_vitl336.pt"))
 
+    # ---- checkpoint ingestion: positional-embedding rescale 24x24 -> 37x37 (model/model.py:395-426), the 518-px setting
+    from model.model import resize_pos_embed as ref_resize
+    from aaclip_b200.clip import resize_pos_embed as our_resize
+    g = torch.Generator().manual_seed(123)
+    old = torch.randn(1 + 24 * 24, 64, generator=g)
+
+    class _V:
+        grid_size = (37, 37)
+
+    class _M:
+        visual = _V()
+
+    sd_ref, sd_our = {"visual.positional_embedding": old.clone()}, {"visual.positional_embedding": old.clone()}
+    ref_resize(sd_ref, _M())
+    our_resize(sd_our, 37)
+    report["pos_embed_resize_maxdiff"] = maxdiff(sd_ref["visual.positional_embedding"], sd_our["visual.positional_embedding"])
+    torch.save({"seed": 123, "old_grid": 24, "new_grid": 37, "width": 64,
+                "resized": sd_ref["visual.positional_embedding"].clone()}, os.path.join(out_dir, "pos_embed_24_to_37.pt"))
+
     json.dump(report, open(os.path.join(out_dir, "oracle_vs_reference.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))
     bad = {k: v for k, v in report.items() if not v < 2e-4}

@@ -72,6 +72,26 @@ def test_dropin_state_dict_keys_match_reference():
     assert full.tokens == 577 and full.mlp_width == 4096
 
 
+def test_pos_embed_resize_matches_reference_golden():
+    """Checkpoint ingestion for the 518-px setting: 24x24 -> 37x37 positional-embedding rescale vs the output of the
+    reference's resize_pos_embed (model/model.py:395-426) stored by oracle/make_golden.py."""
+    from aaclip_b200.clip import CLIP, load_checkpoint, resize_pos_embed
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "pos_embed_24_to_37.pt"), weights_only=False)
+    old = torch.randn(1 + g["old_grid"] ** 2, g["width"], generator=torch.Generator().manual_seed(g["seed"]))
+    sd = {"visual.positional_embedding": old.clone()}
+    assert resize_pos_embed(sd, g["new_grid"])
+    assert sd["visual.positional_embedding"].shape == g["resized"].shape
+    assert (sd["visual.positional_embedding"] - g["resized"]).abs().max().item() < 1e-6
+    assert torch.equal(sd["visual.positional_embedding"][0], old[0])          # class-token row untouched
+    assert not resize_pos_embed(sd, g["new_grid"])                            # already at the target grid
+    # a 336-px state dict loads into a 518-px container through load_checkpoint
+    cfg336, cfg518 = synth.tiny_cfg(image_size=56), synth.tiny_cfg(image_size=84)
+    sd336 = synth.clip_state_dict(cfg336, 0)
+    m518 = CLIP(cfg518)
+    load_checkpoint(m518, sd336)
+    assert m518.visual.positional_embedding.shape == (cfg518.tokens, cfg518.width)
+
+
 def test_weight_map_covers_hot_path():
     from aaclip_b200.engine import weight_map
     cfg = synth.tiny_cfg()
