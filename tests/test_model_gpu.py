@@ -340,3 +340,34 @@ def test_518px_operating_point_vs_oracle():
         assert e_seg <= SEG_TOL and e_det <= SEG_TOL and e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("relu,quick_gelu", [(True, False), (False, True)])
+def test_relu_projections_and_quick_gelu_vs_oracle(relu, quick_gelu):
+    """The two configuration switches the default bench does not exercise: AdaptedCLIP(relu=True) - the ctor default,
+    LeakyReLU after seg_proj / det_proj (model/adapter_modules.py:16-26), in both the materialising and the fused
+    (dots-in-the-epilogue) paths - and QuickGELU (model/transformer.py:46-49) in the c_fc epilogue."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.ModelCfg(layers=3, t_layers=0, image_adapt_until=2, levels=[1, 2, 3], relu=relu, quick_gelu=quick_gelu)
+    sd, ia = synth.clip_state_dict(cfg, 5, text=False), synth.image_adapter_state_dict(cfg, 5)
+    eng = Engine(cfg, device=0, max_batch=2, text=False)
+    try:
+        eng.load_state_dicts(sd, ia, None)
+        img, T = synth.images(2, cfg, seed=13), synth.anchors(cfg, seed=4)
+        seg, det = eng.visual_forward(img.cuda())
+        maps, scores = eng.forward_fused(img.cuda(), T.cuda(), "Industrial")
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            seg_o, det_o = orc.visual_forward(sd, ia, img, layers=3, image_adapt_until=2, levels=(1, 2, 3),
+                                              quick_gelu=quick_gelu)
+            map_o, score_o = orc.predict(seg_o, det_o, T, cfg.image_size, "Industrial")
+        e_seg = max((a.cpu() - b).abs().max().item() for a, b in zip(seg, seg_o))
+        e_map = max((_mm(maps.cpu()[i]) - _mm(map_o[i])).abs().max().item() for i in range(2))
+        e_sc = (scores.cpu() - score_o).abs().max().item()
+        print(f"[relu={relu} quick_gelu={quick_gelu}] seg {e_seg:.3e} normalised map {e_map:.3e} score {e_sc:.3e}")
+        assert e_seg <= SEG_TOL and (det.cpu() - det_o).abs().max().item() <= SEG_TOL
+        assert e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
+    finally:
+        eng.close()
