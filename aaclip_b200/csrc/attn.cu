@@ -57,7 +57,9 @@ constexpr int NSTV = 3;        // V ring depth (V_g waits for P_g: its slot is h
 constexpr int Q_BYTES = BQ * D * 2;      // 16 KB
 constexpr int KV_BYTES = BKV * D * 2;    //  4 KB
 constexpr int P_BYTES = BQ * 128;        // 16 KB: 128 rows x 128 B = two 32-key tiles side by side (double buffer)
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;           // 6 warps; the balanced variant (BAL) runs 8: 4 softmax + 4 control slots
+constexpr int THREADS_BAL = 256;
+constexpr int SOFTMAX_REGS = 96, CTL_REGS = 32;   // BAL: 128 * 96 + 128 * 32 = 256 * 64 (the launch allocation)
 constexpr int TMEM_COLS = 128;           // S0 [0,32) S1 [32,64) O [64,128)
 
 template <int NQ>
@@ -74,6 +76,7 @@ struct Bars {
   uint64_t q_full[2], q_empty[2], k_full[NSTK], v_full[NSTV], k_empty[NSTK], v_empty[NSTV], s_full[2], p_free[2],
       p_full[2];
   uint32_t tmem_slot;
+  uint32_t sm_slot;   // BAL: ordinal (mod 4) of this CTA among the CTAs that started on its SM
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
@@ -93,8 +96,14 @@ __device__ __forceinline__ Item decode_item(int w, int n_qt, int heads, int L, i
   return it;
 }
 
-template <bool TRACE_ON, int POLY, int MINB, int NQ>
-__global__ void __launch_bounds__(THREADS, MINB)
+// BAL: per-SM arrival counters (monotonic; 4 CTAs start per SM per full-size launch, so `& 3` keeps rotating)
+__device__ unsigned int g_sm_arrivals[1024];
+
+// ORD bit 0: hand P_g over (p_full arrive) BEFORE waiting for S_{g+1} instead of after its TMEM load has been issued;
+//     bit 1: the MMA thread issues S_{g+2} ahead of P_g V_g (both become issuable with p_full[g]; the softmax warps
+//            wait for S, nobody waits for PV), at the price of an explicit p_free wait before P half g & 1 is rewritten.
+template <bool TRACE_ON, int POLY, int MINB, int NQ, int BAL, int ORD>
+__global__ void __launch_bounds__(BAL ? THREADS_BAL : THREADS, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, int L, int heads, int causal, int n_items, int n_qt,
                  long long* trace, int trace_cta, float rescale_log2) {
@@ -130,14 +139,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     ptx::tmem_alloc<1>(&bars->tmem_slot, TMEM_COLS);
     ptx::tmem_relinquish<1>();
   }
+  if (BAL && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    bars->sm_slot = atomicAdd(&g_sm_arrivals[smid & 1023u], 1u) & 3u;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_slot);
+  // Control roles.  A CTA-relative warp w always runs on scheduler w % 4 (TMEM lane quarters are tied to it), so with
+  // 6 warps the two single-thread roles of ALL FOUR resident CTAs land on schedulers 0 and 1 and make those two
+  // issue bound while 2 and 3 idle.  BAL: 8 warps (4 softmax + 4 control slots, two of which only park at the final
+  // barrier); the CTA's arrival ordinal on its SM picks which slots carry the MMA issuer and the TMA producer, so
+  // every scheduler of the SM ends up with one of each.  Registers: 64 per thread at launch (256 x 4 CTAs), then
+  // the softmax warpgroup grows to 96 out of what the control warpgroup gives back (32 each).
+  uint32_t mma_warp = 4, tma_warp = 5;
+  if (BAL) {
+    const uint32_t slot = *reinterpret_cast<volatile uint32_t*>(&bars->sm_slot);
+    const uint32_t pair = 4u + ((slot & 1u) << 1), flip = (slot >> 1) & 1u;
+    mma_warp = pair + flip;
+    tma_warp = pair + (flip ^ 1u);
+  }
   ptx::grid_dep_sync();   // everything above overlapped the previous kernel's tail
 
-  if (warp == 5) {
+  if (warp == tma_warp) {
     // ===================================================== TMA producer
+    if (BAL) ptx::reg_dec<CTL_REGS>();
     if (ptx::elect_one()) {
       int kst = 0, vst = 0; uint32_t kph = 0, vph = 0;
       uint32_t n = 0;   // item ordinal of this CTA
@@ -161,8 +189,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == mma_warp) {
     // ===================================================== MMA issuer
+    if (BAL) ptx::reg_dec<CTL_REGS>();
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(BQ, BKV, 0, 0);  // Q K-major, K K-major
       constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32(BQ, D, 0, 1);    // P K-major, V MN-major
@@ -210,6 +239,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (n == 1) TRACE(16, j);
           ptx::mbar_wait_spin(&bars->p_full[g & 1u], (g >> 1) & 1u);  // P_g in smem, S[g&1] drained, O rescaled / drained
           if (n == 1) TRACE(17, j);
+          if (ORD & 2) issue_s();                   // S tile g + 2 first: it is what the softmax warps wait for
           ptx::mbar_wait_spin(&bars->v_full[st], ph);
           ptx::tc_fence_after();
           if (n == 1) TRACE(18, j);
@@ -228,13 +258,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           ptx::mma_commit(&bars->p_free[g & 1u]);   // PV_g has landed in O and has finished reading P half g & 1
           if (++st == NSTV) { st = 0; ph ^= 1u; }
           if (n == 1) TRACE(19, j);
-          issue_s();                                // S tile g + 2 (S[g & 1] was drained before p_full completed)
+          if (!(ORD & 2)) issue_s();                // S tile g + 2 (S[g & 1] was drained before p_full completed)
           if (n == 1) TRACE(20, j);
         }
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ===================================================== softmax warps: thread == query row
+    if (BAL) ptx::reg_inc<SOFTMAX_REGS>();
     const uint32_t quarter = warp & 3u;
     const int row = int(quarter * 32u + lane);
     const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16);
@@ -343,6 +374,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
           }
         }
+        if ((ORD & 2) && g >= 2) {
+          // PV_{g-2} (issued AFTER S_g in this ordering) must have finished reading P half g & 1.  p_free[g & 1]'s next
+          // completion (PV_g) needs this warp's P_g, so the barrier is in the phase of PV_{g-2} or one before it.
+          ptx::mbar_wait(&bars->p_free[half], ((g - 2) >> 1) & 1u);
+        }
         TRS(1);
         float rs;
         if (FAST || four) exp_pass(NG4{}, half, m_used * c, rs);
@@ -389,17 +425,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         l += rs;
         TRS(3);
-        // ---- prefetch the next S tile (possibly the next item's first) while the P hand-over is in flight
-        if (FAST || j + 1 < it.n_kv || more_items) {
-          ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
-          ptx::tc_fence_after();
-          load_scores(g + 1);
+        if (ORD & 1) {
+          ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
+          TRS(4);
+          if (FAST || j + 1 < it.n_kv || more_items) {
+            ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
+            ptx::tc_fence_after();
+            load_scores(g + 1);
+          }
+        } else {
+          // ---- prefetch the next S tile (possibly the next item's first) while the P hand-over is in flight
+          if (FAST || j + 1 < it.n_kv || more_items) {
+            ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
+            ptx::tc_fence_after();
+            load_scores(g + 1);
+          }
+          TRS(4);
+          ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
         }
-        TRS(4);
-        ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
         TRS(5);
         ptx::tmem_ld_wait();
         TRS(6);
@@ -446,6 +495,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     if (store_pending && lane == 0) ptx::bulk_wait<0>();   // smem must outlive the last store's read
+  } else {
+    if (BAL) ptx::reg_dec<CTL_REGS>();   // parked control slots: setmaxnreg is warpgroup-collective
   }
 
   __syncwarp();
@@ -462,13 +513,23 @@ int g_trace_cta = -1;
 
 typedef void (*AttnKern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, int, int, int, int, int, long long*,
                          int, float);
-struct AttnVariant { AttnKern fn; int smem; int ctas_per_sm; };
+struct AttnVariant { AttnKern fn; int smem; int ctas_per_sm; int threads; };
 
+template <int POLY, int ORD>
+AttnVariant pick2(int minb, bool bal) {
+  if (minb == 4 && bal) return {attn::attention_kernel<false, POLY, 4, 1, 1, ORD>, attn::Lay<1>::SMEM_BYTES, 4, attn::THREADS_BAL};
+  if (minb == 4) return {attn::attention_kernel<false, POLY, 4, 1, 0, ORD>, attn::Lay<1>::SMEM_BYTES, 4, attn::THREADS};
+  return {attn::attention_kernel<false, POLY, 3, 2, 0, ORD>, attn::Lay<2>::SMEM_BYTES, 3, attn::THREADS};
+}
 template <int POLY>
-AttnVariant pick(int minb, bool trace) {
-  if (trace) return {attn::attention_kernel<true, 0, 3, 2>, attn::Lay<2>::SMEM_BYTES, 3};
-  if (minb == 4) return {attn::attention_kernel<false, POLY, 4, 1>, attn::Lay<1>::SMEM_BYTES, 4};
-  return {attn::attention_kernel<false, POLY, 3, 2>, attn::Lay<2>::SMEM_BYTES, 3};
+AttnVariant pick(int minb, bool trace, bool bal, int ord) {
+  if (trace) return {attn::attention_kernel<true, 0, 3, 2, 0, 0>, attn::Lay<2>::SMEM_BYTES, 3, attn::THREADS};
+  switch (ord & 3) {
+    case 1: return pick2<POLY, 1>(minb, bal);
+    case 2: return pick2<POLY, 2>(minb, bal);
+    case 3: return pick2<POLY, 3>(minb, bal);
+    default: return pick2<POLY, 0>(minb, bal);
+  }
 }
 }  // namespace
 
@@ -493,11 +554,15 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   static int poly = getenv("AACLIP_ATTN_POLY") ? atoi(getenv("AACLIP_ATTN_POLY")) : 0;
   static int minb = getenv("AACLIP_ATTN_CTAS") ? atoi(getenv("AACLIP_ATTN_CTAS")) : 4;
   static float rescale = getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f;
+  //              AACLIP_ATTN_BAL=<0|1> 8-warp CTAs with the control roles spread over all four schedulers
+  static bool bal = getenv("AACLIP_ATTN_BAL") ? atoi(getenv("AACLIP_ATTN_BAL")) != 0 : false;
+  //              AACLIP_ATTN_ORD=<0..3> hand-over / issue orderings (see the ORD template parameter)
+  static int ord = getenv("AACLIP_ATTN_ORD") ? atoi(getenv("AACLIP_ATTN_ORD")) : 0;
   AttnVariant v;
   switch (poly) {
-    case 0: v = pick<0>(minb, g_trace != nullptr); break;
-    case 1: v = pick<1>(minb, g_trace != nullptr); break;
-    case 2: v = pick<2>(minb, g_trace != nullptr); break;
+    case 0: v = pick<0>(minb, g_trace != nullptr, bal, ord); break;
+    case 1: v = pick<1>(minb, g_trace != nullptr, bal, ord); break;
+    case 2: v = pick<2>(minb, g_trace != nullptr, bal, ord); break;
     default: return host::fail(host::ERR_INVALID, "AACLIP_ATTN_POLY=%d out of range [0,2]", poly);
   }
   static AttnKern configured[16] = {nullptr};
@@ -514,7 +579,7 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   if (items > INT_MAX) return host::fail(host::ERR_INVALID, "attention: %lld work items", items);
   const int sms = host::sm_count(dev);
   const int grid = (int)std::min<long long>(items, (long long)v.ctas_per_sm * (sms > 0 ? sms : 148));
-  AACLIP_CUDA_CHECK(host::launch(v.fn, dim3(grid), dim3(attn::THREADS), (size_t)v.smem, stream, tmQ, tmKV, tmO, L, heads,
+  AACLIP_CUDA_CHECK(host::launch(v.fn, dim3(grid), dim3(v.threads), (size_t)v.smem, stream, tmQ, tmKV, tmO, L, heads,
                                  causal, (int)items, n_qt, g_trace, g_trace_cta, rescale));
   return host::OK;
 }
