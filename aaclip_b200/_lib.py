@@ -63,6 +63,10 @@ SIGNATURES = {
     "aaclip_forward_fused_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "aaclip_submit_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, C.POINTER(_ll)]),
     "aaclip_wait_host": (_i, [_vp, _ll]),
+    "aaclip_preprocess_scratch_bytes": (_ll, [_i, _i, _i, _i]),
+    "aaclip_preprocess_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "aaclip_resize_bicubic_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "aaclip_submit_host_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, C.POINTER(_ll)]),
     "aaclip_text_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "aaclip_text_anchor": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "aaclip_gemm_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),

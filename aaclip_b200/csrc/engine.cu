@@ -129,6 +129,8 @@ struct aaclip_ctx {
   // and copy-out streams, so the H2D of batch k+1 and the D2H of batch k-1 overlap the compute of batch k
   struct HostSlot {
     float *img = nullptr, *maps = nullptr, *scores = nullptr, *anchors = nullptr;
+    uint8_t *raw = nullptr, *raw_scratch = nullptr;   // aaclip_submit_host_u8: raw images and the resample scratch
+    long long raw_cap = 0, raw_scratch_cap = 0;
     cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
     bool busy = false;
     long long ticket = -1;
@@ -368,6 +370,7 @@ extern "C" void aaclip_destroy(aaclip_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (void* p : c->allocs) cudaFree(p);
+  for (auto& sl : c->slots) { if (sl.raw) cudaFree(sl.raw); if (sl.raw_scratch) cudaFree(sl.raw_scratch); }
   if (c->stage) cudaFree(c->stage);
   for (auto& sl : c->slots) {
     if (sl.in_done) cudaEventDestroy(sl.in_done);
@@ -556,10 +559,28 @@ int ensure_host_pipeline(aaclip_ctx* c) {
 }
 }  // namespace
 
+namespace {
+int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host_u8, int H0, int W0, int B,
+                     const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
+                     long long* ticket);
+}
 extern "C" int aaclip_submit_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors, int mode,
                                   float* host_maps_out, float* host_scores_out, long long* ticket) {
+  if (!host_image) return host::fail(host::ERR_INVALID, "submit_host: null argument");
+  return submit_host_impl(c, host_image, nullptr, 0, 0, B, host_anchors, mode, host_maps_out, host_scores_out, ticket);
+}
+extern "C" int aaclip_submit_host_u8(aaclip_ctx* c, const uint8_t* host_u8, int B, int H0, int W0,
+                                     const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
+                                     long long* ticket) {
+  if (!host_u8 || H0 < 1 || W0 < 1) return host::fail(host::ERR_INVALID, "submit_host_u8: null image or bad size");
+  return submit_host_impl(c, nullptr, host_u8, H0, W0, B, host_anchors, mode, host_maps_out, host_scores_out, ticket);
+}
+namespace {
+int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host_u8, int H0, int W0, int B,
+                     const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
+                     long long* ticket) {
   TRY(check_ready(c));
-  if (!host_image || !host_anchors || !ticket) return host::fail(host::ERR_INVALID, "submit_host: null argument");
+  if (!host_anchors || !ticket) return host::fail(host::ERR_INVALID, "submit_host: null argument");
   if (B < 1 || B > c->cfg.max_batch)
     return host::fail(host::ERR_INVALID, "submit_host: B=%d outside [1, max_batch=%d]", B, c->cfg.max_batch);
   if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
@@ -573,10 +594,32 @@ extern "C" int aaclip_submit_host(aaclip_ctx* c, const float* host_image, int B,
   const int S = c->cfg.image_size;
   // copy-in: the slot's previous batch was waited for on the host, so its staging buffers are free
   AACLIP_CUDA_CHECK(cudaMemcpyAsync(sl.anchors, host_anchors, 2LL * c->E * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
-  AACLIP_CUDA_CHECK(cudaMemcpyAsync(sl.img, host_image, 3LL * B * S * S * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+  if (host_u8) {
+    // raw uint8 images: the staging buffers grow to the largest batch seen (the slot is idle: its last ticket was waited for)
+    const long long raw_bytes = 3LL * B * H0 * W0, scratch_bytes = aaclip_preprocess_scratch_bytes(B, H0, W0, S);
+    if (sl.raw_cap < raw_bytes) {
+      if (sl.raw) cudaFree(sl.raw);
+      sl.raw = nullptr; sl.raw_cap = 0;
+      AACLIP_CUDA_CHECK(cudaMalloc(&sl.raw, raw_bytes));
+      sl.raw_cap = raw_bytes;
+    }
+    if (sl.raw_scratch_cap < scratch_bytes) {
+      if (sl.raw_scratch) cudaFree(sl.raw_scratch);
+      sl.raw_scratch = nullptr; sl.raw_scratch_cap = 0;
+      AACLIP_CUDA_CHECK(cudaMalloc(&sl.raw_scratch, scratch_bytes));
+      sl.raw_scratch_cap = scratch_bytes;
+    }
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(sl.raw, host_u8, raw_bytes, cudaMemcpyHostToDevice, c->in_stream));
+  } else {
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(sl.img, host_image, 3LL * B * S * S * sizeof(float), cudaMemcpyHostToDevice, c->in_stream));
+  }
   AACLIP_CUDA_CHECK(cudaEventRecord(sl.in_done, c->in_stream));
   // compute (serial over batches on one stream: the workspaces are shared)
   AACLIP_CUDA_CHECK(cudaStreamWaitEvent(c->own_stream, sl.in_done, 0));
+  if (host_u8) {   // dataset/__init__.py:127-136 on the device
+    TRY(k::launch_preprocess_u8(sl.raw, B, H0, W0, S, nullptr, nullptr, sl.raw_scratch, sl.img, c->own_stream));
+    c->launches += (W0 != S) ? 2 : 1;
+  }
   TRY(aaclip_forward_fused(c, sl.img, B, sl.anchors, mode, host_maps_out ? sl.maps : nullptr,
                            host_scores_out ? sl.scores : nullptr, c->own_stream));
   AACLIP_CUDA_CHECK(cudaEventRecord(sl.comp_done, c->own_stream));
@@ -592,6 +635,7 @@ extern "C" int aaclip_submit_host(aaclip_ctx* c, const float* host_image, int B,
   *ticket = c->next_ticket++;
   return host::OK;
 }
+}  // namespace
 
 extern "C" int aaclip_wait_host(aaclip_ctx* c, long long ticket) {
   TRY(check_ready(c));

@@ -60,4 +60,9 @@ int launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_lev
 int launch_scores(const float* det, const float* anchors, int anchors_batched, int B, int E, float* scores,
                   cudaStream_t stream);
 
+// Loader-side transform (dataset/__init__.py:127-136): u8 [B,H0,W0,3] -> PIL-bicubic resize -> /255 -> normalise ->
+// fp32 [B,3,S,S]; scratch: 3*B*H0*S bytes (unused when W0 == S); mean/std: host float[3] or null (CLIP constants).
+int launch_preprocess_u8(const uint8_t* images, int B, int H0, int W0, int S, const float* mean, const float* stdv,
+                         uint8_t* scratch, float* out, cudaStream_t stream);
+
 }  // namespace k

@@ -200,19 +200,42 @@ class Engine:
                                           C.byref(ticket)))
         return int(ticket.value)
 
+    def submit_host_u8(self, image_u8: torch.Tensor, anchors: torch.Tensor, maps_out: torch.Tensor,
+                       scores_out: torch.Tensor, domain: str = "Industrial") -> int:
+        """submit_host for RAW images: `image_u8` is a CPU uint8 tensor [B,H0,W0,3] (RGB, as PIL decodes it); the
+        reference's transform_x (dataset/__init__.py:127-136) runs on the device, bit-exact with PIL + torchvision."""
+        if image_u8.is_cuda or image_u8.dtype != torch.uint8 or not image_u8.is_contiguous() or image_u8.dim() != 4 \
+                or image_u8.shape[3] != 3:
+            raise ValueError("submit_host_u8 takes a contiguous uint8 CPU tensor [B,H0,W0,3]")
+        for t in (anchors, maps_out, scores_out):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("submit_host_u8 takes contiguous float32 CPU tensors for anchors and outputs")
+        ticket = C.c_longlong(-1)
+        B, H0, W0, _ = image_u8.shape
+        check(self.lib.aaclip_submit_host_u8(self._ctx, image_u8.data_ptr(), B, H0, W0, anchors.data_ptr(),
+                                             DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr(),
+                                             C.byref(ticket)))
+        return int(ticket.value)
+
     def wait_host(self, ticket: int) -> None:
         check(self.lib.aaclip_wait_host(self._ctx, ticket))
 
     def predict_stream(self, batches, anchors: torch.Tensor, domain: str = "Industrial"):
         """The loop of test.py:get_predictions (test.py:53-99) over an iterable of CPU image batches, pipelined:
         while batch k computes, batch k+1 uploads and batch k-1 downloads.  Yields (maps [B,S,S], scores [B]) as
-        pinned CPU tensors, in order."""
+        pinned CPU tensors, in order.  A batch is either float32 [B,3,S,S] (already transformed, as the reference's
+        DataLoader delivers it) or uint8 [B,H0,W0,3] raw RGB, in which case the loader's transform_x
+        (dataset/__init__.py:127-136) also runs on the device."""
         S = self.cfg.image_size
         anchors = anchors.detach().float().cpu().contiguous()
         pending = []
         for img in batches:
             img = img.detach()
-            if img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous():
+            raw = img.dtype == torch.uint8   # [B,H0,W0,3] undecoded-size RGB bytes: transform_x runs on the device
+            if raw:
+                if img.is_cuda or not img.is_contiguous():
+                    img = img.cpu().contiguous()
+            elif img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous():
                 img = img.float().cpu().contiguous()
             if not img.is_pinned():
                 img = img.pin_memory()
@@ -222,7 +245,8 @@ class Engine:
                 t, keep = pending.pop(0)
                 self.wait_host(t)
                 yield keep[1], keep[2]
-            pending.append((self.submit_host(img, anchors, maps, scores, domain), (img, maps, scores)))
+            submit = self.submit_host_u8 if raw else self.submit_host
+            pending.append((submit(img, anchors, maps, scores, domain), (img, maps, scores)))
         for t, keep in pending:
             self.wait_host(t)
             yield keep[1], keep[2]

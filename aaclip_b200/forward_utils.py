@@ -3,6 +3,7 @@
   calculate_similarity_map     forward_utils.py:196-216   (same signature, same return shapes)
   class_text_embedding         forward_utils.py:153-161   (tokenised prompts -> [768, 2] anchor)
   get_predictions_batch        test.py:80-93               (fused: image batch -> summed maps + image scores)
+  transform_x                  dataset/__init__.py:127-136 (Resize BICUBIC + ToTensor + Normalize, on the device)
 
 String work (prompt tables, BPE tokenizer: dataset/constants.py, model/tokenizer.py) stays with the caller:
 `class_text_embedding` starts from token ids.
@@ -66,3 +67,11 @@ def class_text_embedding(model, tokens_normal: torch.Tensor, tokens_abnormal: to
 def get_predictions_batch(model, image: torch.Tensor, epoch_text_feature: torch.Tensor, domain: str = "Industrial"):
     """One iteration of test.py:get_predictions (lines 80-93) on the fused path: (maps [B,S,S], scores [B])."""
     return model.predict(image, epoch_text_feature, domain)
+
+
+@torch.no_grad()
+def transform_x(images_u8: torch.Tensor, img_size: int) -> torch.Tensor:
+    """The loader's image transform (dataset/__init__.py:127-136: transforms.Resize((S,S), Image.BICUBIC), ToTensor,
+    Normalize with the CLIP statistics) for a batch of equally sized raw RGB images uint8 [B,H0,W0,3] on the device;
+    returns float32 [B,3,S,S], bit-exact with what the reference's dataset returns."""
+    return ops.preprocess_u8(images_u8.contiguous(), int(img_size))

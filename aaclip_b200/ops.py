@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_GELU_ERF, ACT_LEAKY, ACT_NONE, ACT_QUICK_GELU, HEAD_TEST_INDUSTRIAL, HEAD_TEST_MEDICAL,
                    HEAD_TRAIN_SOFTMAX, OUT_BF16, OUT_F32, OUT_F32_PATCH, OUT_F32_RESID, check, cur_stream, ptr)
 
-__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head",
+__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head", "preprocess_u8", "resize_bicubic_u8",
            "ACT_NONE", "ACT_GELU_ERF", "ACT_QUICK_GELU", "ACT_LEAKY",
            "OUT_BF16", "OUT_F32", "OUT_F32_RESID", "OUT_F32_PATCH",
            "HEAD_TEST_INDUSTRIAL", "HEAD_TEST_MEDICAL", "HEAD_TRAIN_SOFTMAX"]
@@ -118,3 +118,36 @@ def anomaly_head(seg: Sequence[torch.Tensor], anchors: torch.Tensor, img_size: i
     check(_lib.load().aaclip_anomaly_head(arr, n, int(is_bf16), ptr(anchors), int(batched), ptr(det), B, P, E,
                                           img_size, mode, ptr(maps), ptr(scores), cur_stream()))
     return maps, scores
+
+
+def _check_u8(images: torch.Tensor) -> None:
+    _need(images, torch.uint8, "images")
+    if images.dim() != 4 or images.shape[3] != 3:
+        raise ValueError(f"images must be uint8 [B,H0,W0,3], got {tuple(images.shape)}")
+
+
+def preprocess_u8(images: torch.Tensor, size: int, mean=None, std=None) -> torch.Tensor:
+    """dataset/__init__.py:127-136 on the device: uint8 [B,H0,W0,3] RGB -> PIL-bicubic resize to size x size ->
+    /255 -> (x - mean) / std -> float32 [B,3,size,size], bit-exact with PIL + torchvision."""
+    _check_u8(images)
+    B, H0, W0, _ = images.shape
+    lib = _lib.load()
+    nbytes = int(lib.aaclip_preprocess_scratch_bytes(B, H0, W0, size))
+    scratch = torch.empty(max(nbytes, 1), device=images.device, dtype=torch.uint8)
+    out = torch.empty(B, 3, size, size, device=images.device, dtype=torch.float32)
+    m = (C.c_float * 3)(*mean) if mean is not None else None
+    s = (C.c_float * 3)(*std) if std is not None else None
+    check(lib.aaclip_preprocess_u8(ptr(images), B, H0, W0, size, m, s, ptr(scratch), ptr(out), cur_stream()))
+    return out
+
+
+def resize_bicubic_u8(images: torch.Tensor, size: int) -> torch.Tensor:
+    """PIL.Image.resize((size, size), Image.BICUBIC) on uint8 [B,H0,W0,3] -> uint8 [B,size,size,3], byte-exact."""
+    _check_u8(images)
+    B, H0, W0, _ = images.shape
+    lib = _lib.load()
+    nbytes = int(lib.aaclip_preprocess_scratch_bytes(B, H0, W0, size))
+    scratch = torch.empty(max(nbytes, 1), device=images.device, dtype=torch.uint8)
+    out = torch.empty(B, size, size, 3, device=images.device, dtype=torch.uint8)
+    check(lib.aaclip_resize_bicubic_u8(ptr(images), B, H0, W0, size, ptr(scratch), ptr(out), cur_stream()))
+    return out

@@ -170,6 +170,24 @@ int aaclip_submit_host(aaclip_ctx* ctx, const float* host_image, int B, const fl
                        float* host_maps_out, float* host_scores_out, long long* ticket);
 int aaclip_wait_host(aaclip_ctx* ctx, long long ticket);
 
+/* ---- loader-side image transform (dataset/__init__.py:127-136, :53-62) ------------------------------ */
+/* transforms.Resize((S,S), Image.BICUBIC) + ToTensor + Normalize on the device, bit-exact with PIL + torchvision
+ * (Pillow's fixed-point antialiased resample, IEEE float normalisation).
+ * images: uint8 [B,H0,W0,3] RGB (device); out: fp32 [B,3,S,S]; host_mean / host_std: HOST float[3] or NULL for the
+ * CLIP constants of dataset/__init__.py:130-133; scratch: device, aaclip_preprocess_scratch_bytes() bytes (the
+ * uint8 result of the horizontal pass; may be NULL when W0 == S). */
+long long aaclip_preprocess_scratch_bytes(int B, int H0, int W0, int S);
+int aaclip_preprocess_u8(const uint8_t* images, int B, int H0, int W0, int S, const float* host_mean,
+                         const float* host_std, uint8_t* scratch, float* out, void* stream);
+/* The bare PIL.Image.resize((S,S), BICUBIC): out_u8 uint8 [B,S,S,3] (what transform_mask-style callers and the
+ * parity tests compare byte for byte). */
+int aaclip_resize_bicubic_u8(const uint8_t* images, int B, int H0, int W0, int S, uint8_t* scratch, uint8_t* out_u8,
+                             void* stream);
+/* aaclip_submit_host with RAW images: host_u8 uint8 [B,H0,W0,3]; H2D of the bytes, transform on the device, then
+ * the fused forward.  Same ticket / wait protocol (and the same two slots) as aaclip_submit_host. */
+int aaclip_submit_host_u8(aaclip_ctx* ctx, const uint8_t* host_u8, int B, int H0, int W0, const float* host_anchors,
+                          int mode, float* host_maps_out, float* host_scores_out, long long* ticket);
+
 /* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
 /* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */
 int aaclip_text_forward(aaclip_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);

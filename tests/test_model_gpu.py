@@ -159,6 +159,29 @@ def test_host_pipeline_matches_device_entry(full):
     assert torch.equal(maps, torch.cat([ref[0][0], ref[4][0]])) and torch.equal(scores, torch.cat([ref[0][1], ref[4][1]]))
 
 
+def test_raw_image_pipeline_matches_reference_transform(full):
+    """predict_stream fed RAW uint8 images [B,H0,W0,3]: the loader's transform_x (dataset/__init__.py:127-136) runs
+    on the device inside the pipeline.  The result must be bit-identical to transforming the images with the oracle
+    (pinned to PIL + torchvision) on the host and feeding the float batch - mixed raw sizes, mixed batch kinds."""
+    import numpy as np
+    import preprocess_oracle as po
+    from aaclip_b200 import synth
+    cfg, eng, *_ = full
+    T = synth.anchors(cfg, seed=1)
+    raw = [np.stack([po.synth_image(h, w, 70 + 10 * i + j) for j in range(n)])
+           for i, (n, h, w) in enumerate([(2, 200, 260), (3, 400, 336), (1, 336, 336)])]
+    floats = [torch.from_numpy(np.stack([po.transform_x(im, cfg.image_size) for im in b])).contiguous() for b in raw]
+    ref = []
+    for f in floats:
+        m, s = eng.forward_fused(f.cuda(), T.cuda())
+        ref.append((m.cpu(), s.cpu()))
+    mixed = [torch.from_numpy(raw[0]), floats[1], torch.from_numpy(raw[2]), torch.from_numpy(raw[1])]
+    want = [ref[0], ref[1], ref[2], ref[1]]
+    got = list(eng.predict_stream(mixed, T))
+    for (m, s), (mr, sr) in zip(got, want):
+        assert torch.equal(m, mr) and torch.equal(s, sr)
+
+
 def test_text_path_vs_golden(full):
     import aaclip_oracle as orc
     from aaclip_b200 import synth
