@@ -59,6 +59,7 @@ SIGNATURES = {
     "aaclip_profile_span_ms": (C.c_double, [_vp]),
     "aaclip_visual_forward": (_i, [_vp, _vp, _i, C.POINTER(_vp), _vp, _vp]),
     "aaclip_anomaly_head": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "aaclip_map_minmax": (_i, [_vp, _i, _ll, _vp, _vp]),
     "aaclip_forward_fused": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "aaclip_forward_fused_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "aaclip_submit_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, C.POINTER(_ll)]),

@@ -99,10 +99,13 @@ __device__ __forceinline__ Item decode_item(int w, int n_qt, int heads, int L, i
 // BAL: per-SM arrival counters (monotonic; 4 CTAs start per SM per full-size launch, so `& 3` keeps rotating)
 __device__ unsigned int g_sm_arrivals[1024];
 
-// ORD bit 0: hand P_g over (p_full arrive) BEFORE waiting for S_{g+1} instead of after its TMEM load has been issued;
-//     bit 1: the MMA thread issues S_{g+2} ahead of P_g V_g (both become issuable with p_full[g]; the softmax warps
-//            wait for S, nobody waits for PV), at the price of an explicit p_free wait before P half g & 1 is rewritten.
-template <bool TRACE_ON, int POLY, int MINB, int NQ, int BAL, int ORD>
+// DEEP: S look-ahead of three tiles out of the same two TMEM buffers.  A softmax warp keeps S_g in REGISTERS while it
+//   works on tile g, so buffer g & 1 is free as soon as every warp has loaded it - a whole tile earlier than "P_g is
+//   ready".  The warps therefore complete the TMEM load of S_{g+1} BEFORE the p_full[g] arrive, which then also means
+//   "S_{g+1} is in registers", and the MMA thread issues S_{g+3} (not S_{g+2}) behind P_g V_g.  Price: S_{g+2} is now
+//   issued ahead of P_g V_g, so "S_{g+2} complete" no longer proves that P half g & 1 has been read - an explicit
+//   p_free wait guards the rewrite - and the stale-stabiliser redo works from the register copy (no TMEM reload).
+template <bool TRACE_ON, int POLY, int MINB, int NQ, int BAL, int DEEP>
 __global__ void __launch_bounds__(BAL ? THREADS_BAL : THREADS, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, int L, int heads, int causal, int n_items, int n_qt,
@@ -239,7 +242,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (n == 1) TRACE(16, j);
           ptx::mbar_wait_spin(&bars->p_full[g & 1u], (g >> 1) & 1u);  // P_g in smem, S[g&1] drained, O rescaled / drained
           if (n == 1) TRACE(17, j);
-          if (ORD & 2) issue_s();                   // S tile g + 2 first: it is what the softmax warps wait for
           ptx::mbar_wait_spin(&bars->v_full[st], ph);
           ptx::tc_fence_after();
           if (n == 1) TRACE(18, j);
@@ -258,7 +260,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           ptx::mma_commit(&bars->p_free[g & 1u]);   // PV_g has landed in O and has finished reading P half g & 1
           if (++st == NSTV) { st = 0; ph ^= 1u; }
           if (n == 1) TRACE(19, j);
-          if (!(ORD & 2)) issue_s();                // S tile g + 2 (S[g & 1] was drained before p_full completed)
+          // !DEEP: S tile g + 2 (S[g & 1] was drained before p_full[g] completed)
+          //  DEEP: p_full[g] also says S_{g+1} sits in registers -> S tile g + 3 into buffer (g + 1) & 1; the very
+          //        first hand-over frees both buffers (S_0 consumed, S_1 loaded): S_2 and S_3
+          issue_s();
+          if (DEEP && g == 0) issue_s();
           if (n == 1) TRACE(20, j);
         }
       }
@@ -374,7 +380,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
           }
         }
-        if ((ORD & 2) && g >= 2) {
+        if (DEEP && g >= 2) {
           // PV_{g-2} (issued AFTER S_g in this ordering) must have finished reading P half g & 1.  p_free[g & 1]'s next
           // completion (PV_g) needs this warp's P_g, so the barrier is in the phase of PV_{g-2} or one before it.
           ptx::mbar_wait(&bars->p_free[half], ((g - 2) >> 1) & 1u);
@@ -390,10 +396,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           // S_g is still in TMEM (released by the p_full arrive): reload it, find the true tile max of the rows that
           // tripped the check and restabilise them; every other row keeps its stabiliser (alpha = 1)
           const bool trip = !(rs <= RESCALE_MAX);
-          load_scores(g);
-          ptx::tmem_ld_wait();
           const bool masked = !FAST && ((kv0 + BKV > L) || (causal && kv0 + BKV > it.q0 + 1));
-          if (masked) mask_scores(kv0, it.q0, qi);
+          if (!DEEP) {   // DEEP: S_g's buffer may already hold S_{g+2}; sv (masked in place) is still intact
+            load_scores(g);
+            ptx::tmem_ld_wait();
+            if (masked) mask_scores(kv0, it.q0, qi);
+          }
           const float mt = tile_max(FAST || four);
           const float m_next = trip ? fmaxf(m_used, mt) : m_used;
           const float alpha = ptx::ex2_approx((m_used - m_next) * c);
@@ -413,10 +421,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               ptx::tmem_st_32x32b_x32(t_o + hh * 32, v);
             }
             ptx::tmem_st_wait();
-            // the O loads above overwrote nothing of sv, but the tile is redone from a fresh copy for simplicity
-            load_scores(g);
-            ptx::tmem_ld_wait();
-            if (masked) mask_scores(kv0, it.q0, qi);
+            if (!DEEP) {   // the O loads above overwrote nothing of sv; !DEEP redoes the tile from a fresh copy anyway
+              load_scores(g);
+              ptx::tmem_ld_wait();
+              if (masked) mask_scores(kv0, it.q0, qi);
+            }
           }
           l *= alpha;
           m_used = m_next;
@@ -425,30 +434,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         l += rs;
         TRS(3);
-        if (ORD & 1) {
-          ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
-          TRS(4);
-          if (FAST || j + 1 < it.n_kv || more_items) {
-            ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
-            ptx::tc_fence_after();
-            load_scores(g + 1);
-          }
-        } else {
-          // ---- prefetch the next S tile (possibly the next item's first) while the P hand-over is in flight
-          if (FAST || j + 1 < it.n_kv || more_items) {
-            ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
-            ptx::tc_fence_after();
-            load_scores(g + 1);
-          }
-          TRS(4);
-          ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
+        // ---- prefetch the next S tile (possibly the next item's first) while the P hand-over is in flight
+        if (FAST || j + 1 < it.n_kv || more_items) {
+          ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
+          ptx::tc_fence_after();
+          load_scores(g + 1);
+          if (DEEP) ptx::tmem_ld_wait();   // the arrive below also releases S buffer (g + 1) & 1
         }
+        TRS(4);
+        ptx::fence_proxy_async_smem();  // generic-proxy P stores -> visible to the tensor core (async proxy)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);   // P_g in smem, S[g & 1] drained, O rescaled
         TRS(5);
         ptx::tmem_ld_wait();
         TRS(6);
@@ -515,21 +512,16 @@ typedef void (*AttnKern)(const CUtensorMap, const CUtensorMap, const CUtensorMap
                          int, float);
 struct AttnVariant { AttnKern fn; int smem; int ctas_per_sm; int threads; };
 
-template <int POLY, int ORD>
+template <int POLY, int DEEP>
 AttnVariant pick2(int minb, bool bal) {
-  if (minb == 4 && bal) return {attn::attention_kernel<false, POLY, 4, 1, 1, ORD>, attn::Lay<1>::SMEM_BYTES, 4, attn::THREADS_BAL};
-  if (minb == 4) return {attn::attention_kernel<false, POLY, 4, 1, 0, ORD>, attn::Lay<1>::SMEM_BYTES, 4, attn::THREADS};
-  return {attn::attention_kernel<false, POLY, 3, 2, 0, ORD>, attn::Lay<2>::SMEM_BYTES, 3, attn::THREADS};
+  if (minb == 4 && bal) return {attn::attention_kernel<false, POLY, 4, 1, 1, DEEP>, attn::Lay<1>::SMEM_BYTES, 4, attn::THREADS_BAL};
+  if (minb == 4) return {attn::attention_kernel<false, POLY, 4, 1, 0, DEEP>, attn::Lay<1>::SMEM_BYTES, 4, attn::THREADS};
+  return {attn::attention_kernel<false, POLY, 3, 2, 0, DEEP>, attn::Lay<2>::SMEM_BYTES, 3, attn::THREADS};
 }
 template <int POLY>
-AttnVariant pick(int minb, bool trace, bool bal, int ord) {
+AttnVariant pick(int minb, bool trace, bool bal, int deep) {
   if (trace) return {attn::attention_kernel<true, 0, 3, 2, 0, 0>, attn::Lay<2>::SMEM_BYTES, 3, attn::THREADS};
-  switch (ord & 3) {
-    case 1: return pick2<POLY, 1>(minb, bal);
-    case 2: return pick2<POLY, 2>(minb, bal);
-    case 3: return pick2<POLY, 3>(minb, bal);
-    default: return pick2<POLY, 0>(minb, bal);
-  }
+  return deep ? pick2<POLY, 1>(minb, bal) : pick2<POLY, 0>(minb, bal);
 }
 }  // namespace
 
@@ -556,8 +548,8 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   static float rescale = getenv("AACLIP_ATTN_RESCALE") ? (float)atof(getenv("AACLIP_ATTN_RESCALE")) : 8.0f;
   //              AACLIP_ATTN_BAL=<0|1> 8-warp CTAs with the control roles spread over all four schedulers
   static bool bal = getenv("AACLIP_ATTN_BAL") ? atoi(getenv("AACLIP_ATTN_BAL")) != 0 : false;
-  //              AACLIP_ATTN_ORD=<0..3> hand-over / issue orderings (see the ORD template parameter)
-  static int ord = getenv("AACLIP_ATTN_ORD") ? atoi(getenv("AACLIP_ATTN_ORD")) : 0;
+  //              AACLIP_ATTN_DEEP=<0|1> three-tile S look-ahead (see the DEEP template parameter)
+  static int ord = getenv("AACLIP_ATTN_DEEP") ? atoi(getenv("AACLIP_ATTN_DEEP")) : 0;
   AttnVariant v;
   switch (poly) {
     case 0: v = pick<0>(minb, g_trace != nullptr, bal, ord); break;

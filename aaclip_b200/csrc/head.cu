@@ -541,6 +541,55 @@ extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg
   return host::OK;
 }
 
+// ---- per-image extrema of the anomaly maps: what metrics_eval needs from the pixels for its image-level score
+// (forward_utils.py:241-254: global min-max normalisation, then pmax = max over each image's pixels).  min / max are
+// exact, so the host can combine per-image values over any number of batches.  HBM-bound: 4 * n_pix bytes per image.
+namespace {
+constexpr int MM_THREADS = 1024;
+__global__ void __launch_bounds__(MM_THREADS) map_minmax_kernel(const float* __restrict__ maps, long long n_pix,
+                                                                 float* __restrict__ out) {
+  const float* m = maps + (long long)blockIdx.x * n_pix;
+  float lo = INFINITY, hi = -INFINITY;
+  const bool vec = ((reinterpret_cast<uintptr_t>(m) & 15u) == 0);
+  const long long n4 = vec ? (n_pix >> 2) : 0;
+  const float4* m4 = reinterpret_cast<const float4*>(m);
+  for (long long i = threadIdx.x; i < n4; i += MM_THREADS) {
+    const float4 v = __ldg(m4 + i);
+    lo = fminf(fminf(lo, v.x), fminf(v.y, fminf(v.z, v.w)));
+    hi = fmaxf(fmaxf(hi, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+  }
+  for (long long i = (n4 << 2) + threadIdx.x; i < n_pix; i += MM_THREADS) {
+    const float v = __ldg(m + i);
+    lo = fminf(lo, v); hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float s_lo[MM_THREADS / 32], s_hi[MM_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lo = s_lo[threadIdx.x]; hi = s_hi[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = lo; out[2 * blockIdx.x + 1] = hi; }
+  }
+}
+}  // namespace
+
+extern "C" int aaclip_map_minmax(const float* maps, int B, long long n_pix, float* out, void* stream_) {
+  if (B <= 0) return host::OK;
+  if (!maps || !out || n_pix <= 0) return host::fail(host::ERR_INVALID, "map_minmax: bad argument");
+  map_minmax_kernel<<<B, MM_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(maps, n_pix, out);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
+  return host::OK;
+}
+
 extern "C" int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int col, void* stream_) {
   if (!emb || !anchors || n <= 0 || width <= 0 || (col != 0 && col != 1))
     return host::fail(host::ERR_INVALID, "text_anchor: bad argument");

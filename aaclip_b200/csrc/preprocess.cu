@@ -19,6 +19,8 @@
 #include <limits.h>
 #include <math.h>
 #include <stdarg.h>
+#include <string.h>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -29,7 +31,7 @@
 namespace {
 
 constexpr int PRECISION_BITS = 32 - 8 - 2;
-constexpr int H_ROWS = 4;       // input rows per CTA in the horizontal pass
+constexpr int H_ROWS = 8;       // input rows per CTA in the horizontal pass
 constexpr int H_THREADS = 256;
 constexpr int V_THREADS = 256;
 
@@ -110,12 +112,41 @@ int get_table(int device, int in_size, int out_size, Table* out) {
   return host::OK;
 }
 
+// ToTensor + Normalize as a 3 x 256 table: out = (float(v) / 255 - mean[c]) / std[c], evaluated on the host in IEEE
+// single precision in torch's order (x86-64 SSE float arithmetic == the GPU's __fdiv_rn / __fsub_rn), cached per
+// (device, mean, std) in device memory.
+std::map<std::vector<uint32_t>, float*> g_luts;
+int get_lut(int device, const float* mean, const float* stdv, const float** out) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  std::vector<uint32_t> key(7);
+  key[0] = (uint32_t)device;
+  memcpy(&key[1], mean, 12);
+  memcpy(&key[4], stdv, 12);
+  auto it = g_luts.find(key);
+  if (it != g_luts.end()) { *out = it->second; return host::OK; }
+  std::vector<float> lut(3 * 256);
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) {
+      volatile float t = (float)v / 255.0f;   // volatile: one rounding per operation, no contraction
+      volatile float u = t - mean[c];
+      lut[c * 256 + v] = u / stdv[c];
+    }
+  float* d = nullptr;
+  AACLIP_CUDA_CHECK(cudaMalloc(&d, lut.size() * sizeof(float)));
+  AACLIP_CUDA_CHECK(cudaMemcpy(d, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+  g_luts[key] = d;
+  *out = d;
+  return host::OK;
+}
+
 __device__ __forceinline__ uint32_t clip8(int v) {
   v >>= PRECISION_BITS;   // arithmetic shift, as Pillow's lookup index
   return (uint32_t)min(max(v, 0), 255);
 }
 
-// in u8 [rows, W0, 3] -> out u8 [rows, S, 3]
+// in u8 [rows, W0, 3] -> out u8 [rows, S, 3].  One CTA = H_ROWS input rows; a thread owns output column x for all of
+// them: per tap ONE coefficient load feeds H_ROWS x 3 multiply-adds (taps outer, rows inner: 24 independent
+// accumulators), and the bytes of a row reach shared memory through coalesced 32-bit loads.
 __global__ void __launch_bounds__(H_THREADS)
 resample_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long rows, int W0, int S,
                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
@@ -124,54 +155,103 @@ resample_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, lon
   const int nr = (int)min((long long)H_ROWS, rows - r0);
   const uint8_t* src = in + r0 * W0 * 3;
   const int npx = nr * W0;
-  for (int i = threadIdx.x; i < npx; i += H_THREADS) {
-    const uint8_t* p = src + 3LL * i;
-    px[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+  if ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+    // 4 pixels = 3 words: coalesced word loads, repacked to RGBX
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src);
+    const int nq = npx >> 2;
+    for (int q = threadIdx.x; q < nq; q += (int)blockDim.x) {
+      const uint32_t a = __ldg(w + 3 * q), b = __ldg(w + 3 * q + 1), c = __ldg(w + 3 * q + 2);
+      px[4 * q + 0] = a & 0xFFFFFFu;
+      px[4 * q + 1] = (a >> 24) | ((b & 0xFFFFu) << 8);
+      px[4 * q + 2] = (b >> 16) | ((c & 0xFFu) << 16);
+      px[4 * q + 3] = c >> 8;
+    }
+    for (int i = (nq << 2) + threadIdx.x; i < npx; i += (int)blockDim.x) {
+      const uint8_t* p = src + 3LL * i;
+      px[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    }
+  } else {
+    for (int i = threadIdx.x; i < npx; i += (int)blockDim.x) {
+      const uint8_t* p = src + 3LL * i;
+      px[i] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+    }
   }
   __syncthreads();
   uint8_t* dst = out + r0 * S * 3;
-  for (int o = threadIdx.x; o < nr * S; o += H_THREADS) {
-    const int r = o / S, x = o - r * S;
+  for (int x = threadIdx.x; x < S; x += (int)blockDim.x) {
     const int xmin = __ldg(bounds + 2 * x), cnt = __ldg(bounds + 2 * x + 1);
     const int* k = kk + (long long)x * ksize;
-    const uint32_t* row = px + r * W0 + xmin;
-    int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0;
+    const uint32_t* col = px + xmin;
+    int acc[H_ROWS][3];
+#pragma unroll
+    for (int r = 0; r < H_ROWS; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (PRECISION_BITS - 1);
     for (int t = 0; t < cnt; ++t) {
-      const uint32_t p = row[t];
       const int c = __ldg(k + t);
-      s0 += (int)(p & 255u) * c;
-      s1 += (int)((p >> 8) & 255u) * c;
-      s2 += (int)((p >> 16) & 255u) * c;
+#pragma unroll
+      for (int r = 0; r < H_ROWS; ++r) {
+        // rows past nr read stale smem of this CTA (in bounds); their results are never stored
+        const uint32_t p = col[r * W0 + t];
+        acc[r][0] += (int)(p & 255u) * c;
+        acc[r][1] += (int)((p >> 8) & 255u) * c;
+        acc[r][2] += (int)(p >> 16) * c;
+      }
     }
-    uint8_t* d = dst + 3LL * o;
-    d[0] = (uint8_t)clip8(s0);
-    d[1] = (uint8_t)clip8(s1);
-    d[2] = (uint8_t)clip8(s2);
+#pragma unroll
+    for (int r = 0; r < H_ROWS; ++r) {
+      if (r < nr) {
+        uint8_t* d = dst + 3LL * (r * S + x);
+        d[0] = (uint8_t)clip8(acc[r][0]);
+        d[1] = (uint8_t)clip8(acc[r][1]);
+        d[2] = (uint8_t)clip8(acc[r][2]);
+      }
+    }
   }
 }
 
-// in u8 [B, H0, S, 3] -> out fp32 [B, 3, S, S] (or u8 [B, S, S, 3] when out_u8 != null: the bare PIL resize)
+// in u8 [B, H0, S, 3] -> out fp32 [B, 3, S, S] (or u8 [B, S, S, 3] when out_u8 != null: the bare PIL resize).
+// One CTA = one output row: a thread owns 4 adjacent byte columns (x*3+c), so every tap is one coalesced 32-bit row
+// read (byte loads when the row pitch 3*S is not a multiple of 4); the row's coefficients sit in shared memory.
 __global__ void __launch_bounds__(V_THREADS)
 resample_v_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ out_u8, int H0, int S,
-                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, float m0, float m1, float m2,
-                  float d0, float d1, float d2) {
-  extern __shared__ float plane[];   // [3][S]
+                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, const float* __restrict__ lut) {
+  extern __shared__ float plane[];   // [3][S] floats, then ksize coefficients
+  int* coef = reinterpret_cast<int*>(plane + 3 * S);
   const int y = blockIdx.x, b = blockIdx.y;
   const int ymin = __ldg(bounds + 2 * y), cnt = __ldg(bounds + 2 * y + 1);
-  const int* k = kk + (long long)y * ksize;
+  for (int t = threadIdx.x; t < cnt; t += V_THREADS) coef[t] = __ldg(kk + (long long)y * ksize + t);
+  __syncthreads();
   const int W3 = S * 3;
   const uint8_t* src = in + ((long long)b * H0 + ymin) * W3;
-  for (int j = threadIdx.x; j < W3; j += V_THREADS) {
-    int s = 1 << (PRECISION_BITS - 1);
-    for (int t = 0; t < cnt; ++t) s += (int)__ldg(src + (long long)t * W3 + j) * __ldg(k + t);
+  auto emit = [&](int j, int s) {
     const uint32_t v = clip8(s);
-    const int x = j / 3, c = j - 3 * x;
     if (out_u8) {
       out_u8[((long long)b * S + y) * W3 + j] = (uint8_t)v;
     } else {
-      const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? d0 : (c == 1 ? d1 : d2);
-      // ToTensor: float(v) / 255 ; Normalize: (t - mean) / std  - IEEE ops in this order, as torch's CPU kernels
-      plane[c * S + x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), mean), sd);
+      const int x = j / 3, c = j - 3 * x;
+      plane[c * S + x] = __ldg(lut + c * 256 + v);   // ToTensor + Normalize (see get_lut)
+    }
+  };
+  if ((W3 & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 3u) == 0) {
+    const int W4 = W3 >> 2;
+    const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src);
+    for (int q = threadIdx.x; q < W4; q += V_THREADS) {
+      int s0 = 1 << (PRECISION_BITS - 1), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll 2
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t p = __ldg(src4 + (long long)t * W4 + q);
+        const int c = coef[t];
+        s0 += (int)(p & 255u) * c;
+        s1 += (int)((p >> 8) & 255u) * c;
+        s2 += (int)((p >> 16) & 255u) * c;
+        s3 += (int)(p >> 24) * c;
+      }
+      emit(4 * q, s0); emit(4 * q + 1, s1); emit(4 * q + 2, s2); emit(4 * q + 3, s3);
+    }
+  } else {
+    for (int j = threadIdx.x; j < W3; j += V_THREADS) {
+      int s = 1 << (PRECISION_BITS - 1);
+      for (int t = 0; t < cnt; ++t) s += (int)__ldg(src + (long long)t * W3 + j) * coef[t];
+      emit(j, s);
     }
   }
   if (out_u8) return;
@@ -189,7 +269,7 @@ int run(const uint8_t* images, int B, int H0, int W0, int S, const float* mean, 
   if (H0 < 1 || W0 < 1 || S < 1 || H0 >= (1 << 24) || W0 >= (1 << 24) || S >= (1 << 16))
     return host::fail(host::ERR_INVALID, "preprocess: sizes H0=%d W0=%d S=%d", H0, W0, S);
   const size_t smem_h = (size_t)H_ROWS * W0 * sizeof(uint32_t);
-  if (smem_h > 200 * 1024) return host::fail(host::ERR_INVALID, "preprocess: W0=%d too wide (max 12800)", W0);
+  if (smem_h > 200 * 1024) return host::fail(host::ERR_INVALID, "preprocess: W0=%d too wide (max 6400)", W0);
   if (W0 != S && !scratch) return host::fail(host::ERR_INVALID, "preprocess: scratch of B*H0*S*3 bytes required");
   int dev = 0;
   AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -205,7 +285,10 @@ int run(const uint8_t* images, int B, int H0, int W0, int S, const float* mean, 
     const long long rows = (long long)B * H0;
     const long long grid = (rows + H_ROWS - 1) / H_ROWS;
     if (grid > INT_MAX) return host::fail(host::ERR_INVALID, "preprocess: %lld rows", rows);
-    resample_h_kernel<<<(unsigned)grid, H_THREADS, smem_h, st>>>(images, scratch, rows, W0, S, th.bounds, th.kk, th.ksize);
+    // block size: the S output columns split evenly over ceil(S / 256) passes (336 -> 2 passes of 168 -> 192 threads)
+    const int passes = (S + H_THREADS - 1) / H_THREADS;
+    const int threads = std::min(H_THREADS, (((S + passes - 1) / passes) + 31) / 32 * 32);
+    resample_h_kernel<<<(unsigned)grid, threads, smem_h, st>>>(images, scratch, rows, W0, S, th.bounds, th.kk, th.ksize);
     AACLIP_CUDA_CHECK(cudaGetLastError());
     vin = scratch;
   }
@@ -213,9 +296,11 @@ int run(const uint8_t* images, int B, int H0, int W0, int S, const float* mean, 
   static const float CLIP_STD[3] = {0.26862954f, 0.26130258f, 0.27577711f};
   const float* m = mean ? mean : CLIP_MEAN;
   const float* d = stdv ? stdv : CLIP_STD;
+  const float* lut = nullptr;
+  if (!out_u8) { rc = get_lut(dev, m, d, &lut); if (rc) return rc; }
   if (B > 65535) return host::fail(host::ERR_INVALID, "preprocess: B=%d > 65535", B);
-  resample_v_kernel<<<dim3(S, B), V_THREADS, 3 * (size_t)S * sizeof(float), st>>>(vin, out, out_u8, H0, S, tv.bounds, tv.kk,
-                                                                                  tv.ksize, m[0], m[1], m[2], d[0], d[1], d[2]);
+  resample_v_kernel<<<dim3(S, B), V_THREADS, 3 * (size_t)S * sizeof(float) + (size_t)tv.ksize * sizeof(int), st>>>(vin, out, out_u8, H0, S, tv.bounds, tv.kk,
+                                                                                  tv.ksize, lut);
   AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }

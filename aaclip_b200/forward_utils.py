@@ -4,6 +4,7 @@
   class_text_embedding         forward_utils.py:153-161   (tokenised prompts -> [768, 2] anchor)
   get_predictions_batch        test.py:80-93               (fused: image batch -> summed maps + image scores)
   transform_x                  dataset/__init__.py:127-136 (Resize BICUBIC + ToTensor + Normalize, on the device)
+  map_extrema / image_level_preds   forward_utils.py:241-254 (metrics_eval's min-max normalisation + pmax mix)
 
 String work (prompt tables, BPE tokenizer: dataset/constants.py, model/tokenizer.py) stays with the caller:
 `class_text_embedding` starts from token ids.
@@ -75,3 +76,32 @@ def transform_x(images_u8: torch.Tensor, img_size: int) -> torch.Tensor:
     Normalize with the CLIP statistics) for a batch of equally sized raw RGB images uint8 [B,H0,W0,3] on the device;
     returns float32 [B,3,S,S], bit-exact with what the reference's dataset returns."""
     return ops.preprocess_u8(images_u8.contiguous(), int(img_size))
+
+
+@torch.no_grad()
+def map_extrema(maps: torch.Tensor) -> torch.Tensor:
+    """Per-image (min, max) of a batch of anomaly maps [B,S,S] on the device -> fp32 [B,2].  With these, the
+    image-level half of metrics_eval (forward_utils.py:241-254) needs no pixel data on the host."""
+    return ops.map_minmax(maps.contiguous())
+
+
+def image_level_preds(extrema, image_preds, domain: str = "Industrial"):
+    """metrics_eval's image score (forward_utils.py:241-254) from per-image map extrema [N,2] (all images of the
+    class, any number of batches) and the raw image scores [N]:
+
+        pixel_preds = (p - p.min()) / (p.max() - p.min())   unless p.max() == 1      (:241-244)
+        image_preds = (s - s.min()) / (s.max() - s.min())   unless s.max() == 1      (:245-248)
+        pmax = pixel_preds.max(axis=(1, 2));  image = 0.5 pmax + 0.5 image_preds     (:250-252; Medical: pmax)
+
+    min / max commute with the affine normalisation, so only the extrema are needed.  Host arithmetic on N numbers,
+    in numpy float32 like the reference."""
+    import numpy as np
+    ex = np.asarray(extrema.cpu() if hasattr(extrema, "cpu") else extrema, dtype=np.float32)
+    s = np.asarray(image_preds.cpu() if hasattr(image_preds, "cpu") else image_preds, dtype=np.float32)
+    pmax = ex[:, 1].copy()
+    gmin, gmax = ex[:, 0].min(), ex[:, 1].max()
+    if gmax != 1:
+        pmax = (pmax - gmin) / (gmax - gmin)
+    if s.max() != 1:
+        s = (s - s.min()) / (s.max() - s.min())
+    return pmax * 0.5 + s * 0.5 if domain != "Medical" else pmax

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_GELU_ERF, ACT_LEAKY, ACT_NONE, ACT_QUICK_GELU, HEAD_TEST_INDUSTRIAL, HEAD_TEST_MEDICAL,
                    HEAD_TRAIN_SOFTMAX, OUT_BF16, OUT_F32, OUT_F32_PATCH, OUT_F32_RESID, check, cur_stream, ptr)
 
-__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head", "preprocess_u8", "resize_bicubic_u8",
+__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head", "preprocess_u8", "resize_bicubic_u8", "map_minmax",
            "ACT_NONE", "ACT_GELU_ERF", "ACT_QUICK_GELU", "ACT_LEAKY",
            "OUT_BF16", "OUT_F32", "OUT_F32_RESID", "OUT_F32_PATCH",
            "HEAD_TEST_INDUSTRIAL", "HEAD_TEST_MEDICAL", "HEAD_TRAIN_SOFTMAX"]
@@ -150,4 +150,14 @@ def resize_bicubic_u8(images: torch.Tensor, size: int) -> torch.Tensor:
     scratch = torch.empty(max(nbytes, 1), device=images.device, dtype=torch.uint8)
     out = torch.empty(B, size, size, 3, device=images.device, dtype=torch.uint8)
     check(lib.aaclip_resize_bicubic_u8(ptr(images), B, H0, W0, size, ptr(scratch), ptr(out), cur_stream()))
+    return out
+
+
+def map_minmax(maps: torch.Tensor) -> torch.Tensor:
+    """maps fp32 [B, ...] -> fp32 [B, 2] = per-image (min, max) over all trailing dims (exact)."""
+    _need(maps, torch.float32, "maps")
+    B = maps.shape[0]
+    n_pix = maps.numel() // B if B else 0
+    out = torch.empty(B, 2, device=maps.device, dtype=torch.float32)
+    check(_lib.load().aaclip_map_minmax(ptr(maps), B, n_pix, ptr(out), cur_stream()))
     return out

@@ -153,6 +153,11 @@ int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg_is_bf16, c
                         int anchors_batched, const float* det, int B, int P, int E, int img_size, int mode,
                         float* maps_out, float* scores_out, void* stream);
 
+/* Per-image extrema of anomaly maps: maps fp32 [B, n_pix] -> out fp32 [B][2] = (min, max).  The pixel-side input of
+ * metrics_eval's image-level score (forward_utils.py:241-254: global min-max normalisation + per-image max); exact,
+ * so callers combine them over batches on the host. */
+int aaclip_map_minmax(const float* maps, int B, long long n_pix, float* out, void* stream);
+
 /* ---- fused image -> anomaly map (AdaptedCLIP.forward + head, no seg-token materialisation) ---------- */
 int aaclip_forward_fused(aaclip_ctx* ctx, const float* image, int B, const float* anchors /*[E,2]*/, int mode,
                          float* maps_out /*[B,S,S]*/, float* scores_out /*[B]*/, void* stream);

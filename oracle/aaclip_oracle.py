@@ -195,3 +195,22 @@ def minmax_normalise(maps: torch.Tensor) -> torch.Tensor:
     """forward_utils.py:241-244 (metrics_eval): (x - min) / (max - min) over the whole set."""
     lo, hi = maps.min(), maps.max()
     return (maps - lo) / (hi - lo)
+
+
+def metrics_image_preds(pixel_preds, image_preds, domain: str = "Industrial"):
+    """forward_utils.py:241-254 (the part of metrics_eval in front of the sklearn calls), numpy like the reference:
+    global min-max normalisation of the pixel and image predictions unless their max is exactly 1, per-image pixel
+    maximum, 50/50 mix (Medical: pixel maximum alone).  Returns (normalised pixel_preds, image_preds)."""
+    import numpy as np
+    pixel_preds = np.asarray(pixel_preds)
+    image_preds = np.asarray(image_preds)
+    if pixel_preds.max() != 1:
+        pixel_preds = (pixel_preds - pixel_preds.min()) / (pixel_preds.max() - pixel_preds.min())
+    if image_preds.max() != 1:
+        image_preds = (image_preds - image_preds.min()) / (image_preds.max() - image_preds.min())
+    pmax_pred = pixel_preds.max(axis=(1, 2))
+    if domain != "Medical":
+        image_preds = pmax_pred * 0.5 + image_preds * 0.5
+    else:
+        image_preds = pmax_pred
+    return pixel_preds, image_preds

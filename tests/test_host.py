@@ -149,3 +149,25 @@ def test_gather_scores_gloo_world2(total):
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_image_level_preds_matches_metrics_eval_restatement():
+    """forward_utils.image_level_preds (from per-image map extrema) == the oracle's restatement of
+    metrics_eval's normalisation + pmax mix (forward_utils.py:241-254) on the full pixel arrays."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import aaclip_oracle as orc
+    from aaclip_b200 import forward_utils as fu
+    rng = np.random.RandomState(3)
+    maps = (rng.rand(9, 24, 24).astype(np.float32) * 7 + 1.5)
+    scores = rng.rand(9).astype(np.float32)
+    ex = np.stack([maps.min(axis=(1, 2)), maps.max(axis=(1, 2))], 1)
+    for domain in ("Industrial", "Medical"):
+        _, want = orc.metrics_image_preds(maps, scores, domain)
+        got = fu.image_level_preds(ex, scores, domain)
+        assert np.array_equal(got, want.astype(np.float32))
+    # the reference's "already normalised" branch: max exactly 1 leaves the values alone
+    maps1 = maps / maps.max()
+    ex1 = np.stack([maps1.min(axis=(1, 2)), maps1.max(axis=(1, 2))], 1)
+    _, want = orc.metrics_image_preds(maps1, scores, "Industrial")
+    assert np.array_equal(fu.image_level_preds(ex1, scores, "Industrial"), want.astype(np.float32))

@@ -183,3 +183,19 @@ def test_attention(B, L, heads, causal):
     err, rel = _report(f"attn B{B} L{L} h{heads} causal={causal}", out, ref)
     assert not torch.isnan(out.float()).any()
     assert rel < 1.5e-2  # P and the output are bf16
+
+
+@pytest.mark.parametrize("B,n", [(64, 336 * 336), (3, 518 * 518), (5, 1001), (1, 1)])
+def test_map_minmax(B, n):
+    """aaclip_map_minmax: per-image extrema, exact (min / max do not round); odd sizes take the scalar tail."""
+    from aaclip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + n)
+    m = torch.randn(B, n, device="cuda", generator=g) * 3 + 1
+    got = ops.map_minmax(m)
+    assert torch.equal(got[:, 0], m.amin(1)) and torch.equal(got[:, 1], m.amax(1))
+    if n > 8:   # a view that is not 16-byte aligned takes the scalar path
+        mm = m[:, 1:].contiguous()
+        v = torch.empty(B * (n - 1) + 1, device="cuda")[1:].view(B, n - 1)
+        v.copy_(mm)
+        g2 = ops.map_minmax(v)
+        assert torch.equal(g2[:, 0], mm.amin(1)) and torch.equal(g2[:, 1], mm.amax(1))
