@@ -40,7 +40,7 @@ class AaclipCfg(C.Structure):
         ("n_levels", C.c_int), ("levels", C.c_int * 8), ("proj_relu", C.c_int),
         ("t_context", C.c_int), ("t_vocab", C.c_int), ("t_width", C.c_int), ("t_heads", C.c_int),
         ("t_layers", C.c_int), ("text_adapt_until", C.c_int), ("text_adapt_weight", C.c_float),
-        ("max_batch", C.c_int), ("max_text", C.c_int), ("cta_group", C.c_int),
+        ("max_batch", C.c_int), ("max_text", C.c_int), ("cta_group", C.c_int), ("ln_fold", C.c_int),
     ]
 
 
@@ -71,6 +71,10 @@ SIGNATURES = {
     "aaclip_text_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "aaclip_text_anchor": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "aaclip_gemm_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "aaclip_gemm_resid_ln": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "aaclip_gemm_lnfold": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
+    "aaclip_rowstats_cast": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp]),
+    "aaclip_fold_ln_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "aaclip_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),
     "aaclip_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "aaclip_attention_trace": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -78,6 +78,10 @@ __global__ void eot_gather_kernel(const int32_t* __restrict__ tokens, const floa
 }
 
 struct LayerW {
+  // folded-LayerNorm schedule (visual tower): fp32 masters of the two Linears that consume a LayerNorm, their
+  // gamma-folded bf16 form, the column sums of the folded weights and the beta-folded biases
+  float *qkv_w32 = nullptr, *fc_w32 = nullptr, *qkv_cs = nullptr, *qkv_bf = nullptr, *fc_cs = nullptr, *fc_bf = nullptr;
+  bf16 *qkv_wf = nullptr, *fc_wf = nullptr;
   bf16 *qkv_w = nullptr, *out_w = nullptr, *fc_w = nullptr, *proj_w = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *qkv_b = nullptr, *out_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr,
         *fc_b = nullptr, *proj_b = nullptr;
@@ -107,6 +111,9 @@ struct aaclip_ctx {
   int device = 0;
   int G = 0, P = 0, L = 0, Kpad = 0, E = 0;
   int cta_group = 2;
+  // LayerNorm folded into the consumer GEMMs of the visual tower (see gemm_sm100.cuh); AACLIP_LN_FOLD=0 disables it
+  bool ln_fold = true, fold_dirty = true;
+  float2* part = nullptr;   // [rows][width / 128] (sum, sum of squares) per 128-column slice of the fp32 rows
   long long bytes = 0;
   long long launches = 0;
   std::vector<void*> allocs;
@@ -230,6 +237,54 @@ int run_block(aaclip_ctx* c, const Tower& t, int i, int B, int L, int causal, fl
   return host::OK;
 }
 
+// (Re)build the folded weights of the visual tower after any of their sources changed.
+int refold(aaclip_ctx* c, cudaStream_t st) {
+  if (!c->ln_fold || !c->fold_dirty) return host::OK;
+  const int w = c->v.width, ff = c->v.mlp;
+  for (auto& l : c->v.lw) {
+    TRY(k::launch_fold_ln_weight(l.qkv_w32, l.qkv_b, l.ln1_g, l.ln1_b, 3 * w, w, l.qkv_wf, l.qkv_cs, l.qkv_bf, st));
+    TRY(k::launch_fold_ln_weight(l.fc_w32, l.fc_b, l.ln2_g, l.ln2_b, ff, w, l.fc_wf, l.fc_cs, l.fc_bf, st));
+    c->launches += 2;
+  }
+  c->fold_dirty = false;
+  return host::OK;
+}
+
+// One block of the visual tower on the folded-LayerNorm schedule: on entry xn holds the bf16 copy of x and `part`
+// its per-slice (sum, sum of squares); both are left in that state for the next block.  No LayerNorm launches:
+//   qkv  = rstd (xb Wf_qkv^T - mean s) + b'        (consumer epilogue)
+//   x   += att W_out^T + b, xb, part               (producer epilogue)
+//   h    = GELU(rstd (xb Wf_fc^T - mean s) + b')
+//   x   += h W_proj^T + b, xb, part
+//   adapter layers: a = LeakyReLU(xb W_a^T) straight from the bf16 copy (no cast), then the mix rewrites x, xb, part
+int run_block_fold(aaclip_ctx* c, const Tower& t, int i, int B, int L, float adapt_w, cudaStream_t st) {
+  const LayerW& l = t.lw[i];
+  const int rows = B * L, w = t.width, ff = t.mlp, slices = w / 128;
+  const int cg = c->cta_group;
+  k::LnFold cons;
+  cons.part_in = c->part; cons.slices = slices; cons.eps = 1e-5f;
+  k::LnFold prod;
+  prod.xb = c->xn; prod.ldxb = w; prod.part_out = c->part;
+  cons.colsum = l.qkv_cs;
+  RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_wf, w, rows, 3 * w, w, l.qkv_bf, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
+                     nullptr, 0, cg, st, nullptr, nullptr, 0, &cons));
+  RUN(PC_ATTENTION, k::launch_attention(c->qkv, c->att, B, L, t.heads, 0, st));
+  RUN(PC_GEMM_OUT, k::launch_gemm(c->att, w, l.out_w, w, rows, w, w, l.out_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID_LN,
+                     nullptr, 0, cg, st, nullptr, nullptr, 0, &prod));
+  cons.colsum = l.fc_cs;
+  RUN(PC_GEMM_FC, k::launch_gemm(c->xn, w, l.fc_wf, w, rows, ff, w, l.fc_bf, c->h, ff, c->cfg.act, gemm::OUT_BF16, nullptr, 0, cg,
+                     st, nullptr, nullptr, 0, &cons));
+  RUN(PC_GEMM_PROJ, k::launch_gemm(c->h, ff, l.proj_w, ff, rows, w, ff, l.proj_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID_LN,
+                     nullptr, 0, cg, st, nullptr, nullptr, 0, &prod));
+  if (i < (int)t.adapters.size()) {
+    RUN(PC_GEMM_ADAPTER, k::launch_gemm(c->xn, w, t.adapters[i], w, rows, w, w, nullptr, c->a, w, gemm::ACT_LEAKY, gemm::OUT_F32,
+                       nullptr, 0, cg, st));
+    RUN(PC_ADAPTER_MIX, k::launch_adapter_mix(c->x, c->a, adapt_w, rows, w, nullptr, nullptr, 1e-5f, nullptr, st, c->xn, c->part,
+                              slices));
+  }
+  return host::OK;
+}
+
 // seg_out[level] (fp32 [B,P,E], optional), det_out (fp32 [B,E], optional), dots (optional, [levels][B*P][2] with
 // anchors) for one chunk of B <= max_batch images.
 int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out, long long seg_off, float* det_out,
@@ -245,8 +300,14 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
   RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, nullptr, c->x, st));
   bool xn_ready = false;
   int level = 0;
+  const bool fold = c->ln_fold;
+  if (fold) {
+    TRY(refold(c, st));
+    RUN(PC_CAST, k::launch_rowstats_cast(c->x, rows, w, c->xn, c->part, w / 128, st));
+  }
   for (int i = 0; i < cfg.layers; ++i) {
-    TRY(run_block(c, c->v, i, B, L, 0, cfg.image_adapt_weight, &xn_ready, st));
+    if (fold) TRY(run_block_fold(c, c->v, i, B, L, cfg.image_adapt_weight, st));
+    else TRY(run_block(c, c->v, i, B, L, 0, cfg.image_adapt_weight, &xn_ready, st));
     if (level < cfg.n_levels && cfg.levels[level] == i + 1) {
       const bool last = (level == cfg.n_levels - 1);
       // tap: x[:, 1:, :] -> ln_post -> seg_proj (and det_proj on the last tap)   (model/adapter.py:100-111)
@@ -338,6 +399,17 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
   auto A = [&](int r) { if (rc == host::OK) rc = r; };
   c->v.width = cfg->width; c->v.heads = cfg->heads; c->v.layers = cfg->layers; c->v.mlp = cfg->mlp_width;
   A(alloc_tower(c, c->v, cfg->image_adapt_until));
+  c->ln_fold = cfg->ln_fold == 1 ? true : cfg->ln_fold == 2 ? false
+               : (getenv("AACLIP_LN_FOLD") ? atoi(getenv("AACLIP_LN_FOLD")) != 0 : true);
+  if (w % 256 != 0 || w / 128 > 32) c->ln_fold = false;
+  if (c->ln_fold) {
+    const long long ffv = cfg->mlp_width;
+    for (auto& l : c->v.lw) {
+      A(c->alloc(&l.qkv_w32, 3 * w * w)); A(c->alloc(&l.fc_w32, ffv * w));
+      A(c->alloc(&l.qkv_wf, 3 * w * w)); A(c->alloc(&l.fc_wf, ffv * w));
+      A(c->alloc(&l.qkv_cs, 3 * w)); A(c->alloc(&l.qkv_bf, 3 * w)); A(c->alloc(&l.fc_cs, ffv)); A(c->alloc(&l.fc_bf, ffv));
+    }
+  }
   A(c->alloc(&c->conv_w, w * c->Kpad)); A(c->alloc(&c->cls, w)); A(c->alloc(&c->pos, (long long)c->L * w));
   A(c->alloc(&c->ln_pre_g, w)); A(c->alloc(&c->ln_pre_b, w)); A(c->alloc(&c->ln_post_g, w)); A(c->alloc(&c->ln_post_b, w));
   c->segdet_w.resize(cfg->n_levels);
@@ -360,6 +432,7 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
   A(c->alloc(&c->col, prow * c->Kpad)); A(c->alloc(&c->tap, prow * w)); A(c->alloc(&c->s, prow * 2 * E));
   A(c->alloc(&c->dots, (long long)cfg->n_levels * prow * 2)); A(c->alloc(&c->det, (long long)cfg->max_batch * E)); A(c->alloc(&c->rownorm, prow));
   A(c->alloc(&c->partials, (long long)cfg->n_levels * prow * ((E + 127) / 128) * 4));
+  if (c->ln_fold) A(c->alloc(&c->part, rows * (w / 128)));
   if (rc != host::OK) { aaclip_destroy(c); return rc; }
   *out = c;
   return host::OK;
@@ -489,6 +562,18 @@ extern "C" int aaclip_set_weight(aaclip_ctx* c, int id, int layer, const float* 
     }
     AACLIP_CUDA_CHECK(cudaMemcpyAsync(c->stage, src, numel * sizeof(float), cudaMemcpyHostToDevice, st));
     dsrc = c->stage;
+  }
+  if (c->ln_fold && !is_t) {
+    float* master = nullptr;
+    if (id == AACLIP_W_V_QKV_W) master = c->v.lw[layer].qkv_w32;
+    if (id == AACLIP_W_V_FC_W) master = c->v.lw[layer].fc_w32;
+    if (master) AACLIP_CUDA_CHECK(cudaMemcpyAsync(master, dsrc, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    switch (id) {
+      case AACLIP_W_V_LN1_G: case AACLIP_W_V_LN1_B: case AACLIP_W_V_QKV_W: case AACLIP_W_V_QKV_B:
+      case AACLIP_W_V_LN2_G: case AACLIP_W_V_LN2_B: case AACLIP_W_V_FC_W: case AACLIP_W_V_FC_B:
+        c->fold_dirty = true; break;
+      default: break;
+    }
   }
   if (!to_bf16) {
     AACLIP_CUDA_CHECK(cudaMemcpyAsync(dst, dsrc, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));

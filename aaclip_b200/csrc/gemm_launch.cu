@@ -7,11 +7,11 @@
 
 namespace {
 
-template <int CG, int ACT, int OUT>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const gemm::Args& args, int num_sms,
-               cudaStream_t stream) {
-  using C = gemm::Cfg<CG>;
-  auto kern = gemm::gemm_kernel<CG, ACT, OUT>;
+template <int CG, int ACT, int OUT, int LNF = 0>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD,
+               const gemm::Args& args, int num_sms, cudaStream_t stream) {
+  using C = gemm::Cfg<CG, OUT == gemm::OUT_F32_RESID_LN>;
+  auto kern = gemm::gemm_kernel<CG, ACT, OUT, LNF>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     AACLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -34,21 +34,31 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = host::pdl_enabled() ? 2 : 1;
-  AACLIP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, args));
+  AACLIP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, args));
   return host::OK;
 }
 
 template <int CG>
 int dispatch(int act, int out_mode, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-             const gemm::Args& a, int sms,
-             cudaStream_t s) {
+             const CUtensorMap& tmD, const gemm::Args& a, int sms, cudaStream_t s) {
   using namespace gemm;
+  if (a.ln_part != nullptr) {   // LayerNorm folded into this (consumer) GEMM: bf16 outputs only
+#define CASE_LN(A_) \
+  if (act == A_ && out_mode == OUT_BF16) return launch_one<CG, A_, OUT_BF16, 1>(tmA, tmB, tmC, tmD, a, sms, s);
+    CASE_LN(ACT_NONE)
+    CASE_LN(ACT_GELU_ERF)
+    CASE_LN(ACT_QUICK_GELU)
+#undef CASE_LN
+    return host::fail(host::ERR_INVALID, "gemm: the folded-LayerNorm epilogue exists for bf16 outputs only (act=%d, out=%d)",
+                      act, out_mode);
+  }
 #define CASE(A_, O_) \
-  if (act == A_ && out_mode == O_) return launch_one<CG, A_, O_>(tmA, tmB, tmC, a, sms, s);
+  if (act == A_ && out_mode == O_) return launch_one<CG, A_, O_>(tmA, tmB, tmC, tmD, a, sms, s);
   CASE(ACT_NONE, OUT_BF16)
   CASE(ACT_GELU_ERF, OUT_BF16)
   CASE(ACT_QUICK_GELU, OUT_BF16)
   CASE(ACT_NONE, OUT_F32_RESID)
+  CASE(ACT_NONE, OUT_F32_RESID_LN)
   CASE(ACT_NONE, OUT_F32)
   CASE(ACT_LEAKY, OUT_F32)
   CASE(ACT_NONE, OUT_F32_PATCH)
@@ -62,7 +72,7 @@ int dispatch(int act, int out_mode, const CUtensorMap& tmA, const CUtensorMap& t
 
 int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out,
                    int ldo, int act, int out_mode, const float* pos, int P, int cta_group, cudaStream_t stream,
-                   const float* anchors, void* partials, int dots_cols) {
+                   const float* anchors, void* partials, int dots_cols, const k::LnFold* ln) {
   if (M <= 0 || N <= 0 || K <= 0) return host::fail(host::ERR_INVALID, "gemm: empty problem %dx%dx%d", M, N, K);
   if (N % 32 != 0) return host::fail(host::ERR_INVALID, "gemm: N=%d must be a multiple of 32", N);
   if (lda % 8 != 0 || ldw % 8 != 0 || lda < K || ldw < K)
@@ -74,6 +84,11 @@ int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N,
                                      out == nullptr))
     return host::fail(host::ERR_INVALID, "gemm: dots epilogue needs anchors, partials and dots_cols %% 128 == 0 (got %d)",
                       dots_cols);
+  const bool rln = (out_mode == gemm::OUT_F32_RESID_LN);
+  if (rln && (!ln || !ln->xb || !ln->part_out || N % 256 != 0 || ln->ldxb % 8 != 0 || ln->ldxb < N))
+    return host::fail(host::ERR_INVALID, "gemm: the residual+statistics epilogue needs xb, part_out and N %% 256 == 0");
+  if (!rln && ln && ln->part_in && (!ln->colsum || ln->slices <= 0 || out_mode != gemm::OUT_BF16))
+    return host::fail(host::ERR_INVALID, "gemm: the folded-LayerNorm epilogue needs colsum, slices and a bf16 output");
   int dev = 0;
   AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
   const int sms = host::sm_count(dev);
@@ -83,8 +98,9 @@ int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N,
   rc = host::make_tmap_2d(&tmB, W, N, K, ldw, cta_group == 1 ? 256 : 128);
   if (rc) return rc;
   // output tiles leave through TMA: box = 32 rows x 128 B (64 bf16 / 32 fp32), 128B swizzle
-  CUtensorMap tmC;
+  CUtensorMap tmC, tmD;
   memset(&tmC, 0, sizeof tmC);
+  memset(&tmD, 0, sizeof tmD);
   if (out_mode != gemm::OUT_F32_PATCH && !(out_mode == gemm::OUT_DOTS && out == nullptr)) {
     const bool obf = (out_mode == gemm::OUT_BF16);
     if (ldo % (obf ? 8 : 4) != 0 || ldo < N) return host::fail(host::ERR_INVALID, "gemm: output pitch %d", ldo);
@@ -94,8 +110,17 @@ int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N,
   gemm::Args a;
   a.M = M; a.N = N; a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.pos = pos; a.P = P;
   a.anchors = anchors; a.partials = static_cast<float4*>(partials); a.dots_cols = dots_cols;
-  return cta_group == 1 ? dispatch<1>(act, out_mode, tmA, tmB, tmC, a, sms, stream)
-                        : dispatch<2>(act, out_mode, tmA, tmB, tmC, a, sms, stream);
+  a.ln_part = nullptr; a.ln_slices = 0; a.ln_width = K; a.ln_eps = 0.f; a.ln_colsum = nullptr; a.part_out = nullptr;
+  if (rln) {
+    rc = host::make_tmap_out(&tmD, ln->xb, M, N, ln->ldxb, true);
+    if (rc) return rc;
+    a.part_out = static_cast<float2*>(ln->part_out);
+  } else if (ln && ln->part_in) {
+    a.ln_part = static_cast<const float2*>(ln->part_in);
+    a.ln_slices = ln->slices; a.ln_eps = ln->eps; a.ln_colsum = ln->colsum;
+  }
+  return cta_group == 1 ? dispatch<1>(act, out_mode, tmA, tmB, tmC, tmD, a, sms, stream)
+                        : dispatch<2>(act, out_mode, tmA, tmB, tmC, tmD, a, sms, stream);
 }
 
 extern "C" int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
@@ -104,4 +129,23 @@ extern "C" int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, 
   if (out_mode == gemm::OUT_DOTS) return host::fail(host::ERR_INVALID, "gemm: the dots epilogue is internal to the engine");
   return k::launch_gemm(A, lda, W, ldw, M, N, K, bias, out, ldo, act, out_mode, pos, P, cta_group,
                         static_cast<cudaStream_t>(stream));
+}
+
+// Building blocks of the folded-LayerNorm schedule, exported so the parity tests can pin them on their own:
+//   aaclip_gemm_resid_ln  x <- x + A W^T + bias (fp32, in place); xb <- bf16(x); part[r][N/128] <- (sum, sum sq) per slice
+//   aaclip_gemm_lnfold    out(bf16) <- act(rstd_r (A Wf^T - mean_r colsum) + bias) with the row statistics from part
+extern "C" int aaclip_gemm_resid_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
+                                    float* x, int ldx, void* xb, int ldxb, void* part_out, int cta_group, void* stream) {
+  k::LnFold ln;
+  ln.xb = xb; ln.ldxb = ldxb; ln.part_out = part_out;
+  return k::launch_gemm(A, lda, W, ldw, M, N, K, bias, x, ldx, gemm::ACT_NONE, gemm::OUT_F32_RESID_LN, nullptr, 0, cta_group,
+                        static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, &ln);
+}
+extern "C" int aaclip_gemm_lnfold(const void* A, int lda, const void* Wf, int ldw, int M, int N, int K, const float* bias,
+                                  const float* colsum, const void* part, int slices, float eps, void* out, int ldo, int act,
+                                  int cta_group, void* stream) {
+  k::LnFold ln;
+  ln.part_in = part; ln.slices = slices; ln.eps = eps; ln.colsum = colsum;
+  return k::launch_gemm(A, lda, Wf, ldw, M, N, K, bias, out, ldo, act, gemm::OUT_BF16, nullptr, 0, cta_group,
+                        static_cast<cudaStream_t>(stream), nullptr, nullptr, 0, &ln);
 }

@@ -28,7 +28,7 @@
 namespace gemm {
 
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_QUICK_GELU = 2, ACT_LEAKY = 3 };
-enum Out : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_RESID = 2, OUT_F32_PATCH = 3, OUT_DOTS = 4 };
+enum Out : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_RESID = 2, OUT_F32_PATCH = 3, OUT_DOTS = 4, OUT_F32_RESID_LN = 5 };
 
 struct Args {
   int M, N, K;
@@ -43,22 +43,33 @@ struct Args {
   const float* anchors;   // [dots_cols, 2]
   float4* partials;       // [M][dots_cols / 128]
   int dots_cols;          // multiple of 128
+  // LayerNorm folded into the CONSUMER GEMM (template LNF):  LN(x) W^T + b  ==  rstd_r (x (W o gamma)^T - mean_r s) + b'
+  // with s[n] = sum_k (W o gamma)[n,k], b' = b + W beta.  A is the bf16 copy of the fp32 rows, W the folded weight,
+  // bias = b'; the row statistics come from the partial sums the producer left per 128-column slice.
+  const float2* ln_part;  // [M][ln_slices] (sum, sum of squares) of the fp32 rows
+  int ln_slices;
+  int ln_width;           // row width the statistics run over (= K)
+  float ln_eps;
+  const float* ln_colsum; // s[N]
+  // OUT_F32_RESID_LN (the PRODUCER): out <- out + acc + bias (fp32, in place through TMA load / store), plus the bf16
+  // copy of the new rows (tensor map tmD) and their per-slice partial sums
+  float2* part_out;       // [M][N / 128]
 };
 
-template <int CG>
+template <int CG, bool RLN = false>   // RLN: the OUT_F32_RESID_LN epilogue (8 KB of staging per warp, one stage fewer)
 struct Cfg {
   static constexpr int BM = 128;           // accumulator rows per CTA (== TMEM lanes)
   static constexpr int BN = 256;           // tile N (per CTA pair when CG == 2)
   static constexpr int BN_CTA = BN / CG;   // rows of W staged by each CTA
   static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
   static constexpr int UMMA_K = 16;
-  static constexpr int STAGES = (CG == 1) ? 4 : 6;
+  static constexpr int STAGES = RLN ? ((CG == 1) ? 3 : 5) : ((CG == 1) ? 4 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int NUM_EPI_WARPS = 8;
-  static constexpr int STAGING_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled
+  static constexpr int STAGING_BYTES = (RLN ? 2 : 1) * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled (RLN: X + Y)
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int THREADS = 128 + NUM_EPI_WARPS * 32;
@@ -84,6 +95,47 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // x * sigmoid(1.702 x)  (model/transformer.py:46-49)
 __device__ __forceinline__ float quick_gelu(float x) {
   return x * ptx::rcp_approx(1.0f + ptx::ex2_approx(-1.702f * 1.4426950408889634f * x));
+}
+
+// Packed (two fp32 lanes per instruction: FFMA2 / FMUL2 / FADD2) forms of the same functions: the c_fc epilogue is
+// FMA-pipe bound (12 FMA-pipe instructions per element of GELU against an 8192-cycle mainloop per tile), the packed
+// forms halve that.
+__device__ __forceinline__ ptx::F2 gelu_erf2(ptx::F2 x) {
+  using namespace ptx;
+  const F2 ax = abs2(x);
+  float d0, d1;
+  f2_get(fma2(ax, f2s(0.3275911f * 0.70710678118654752f), f2s(1.0f)), d0, d1);
+  const F2 t = f2(rcp_approx(d0), rcp_approx(d1));
+  F2 p = fma2(t, f2s(1.061405429f), f2s(-1.453152027f));
+  p = fma2(p, t, f2s(1.421413741f));
+  p = fma2(p, t, f2s(-0.284496736f));
+  p = fma2(p, t, f2s(0.254829592f));
+  p = mul2(p, t);
+  float e0, e1;
+  f2_get(mul2(mul2(x, f2s(-0.5f * 1.4426950408889634f)), x), e0, e1);   // -x^2/2 * log2(e)
+  const F2 e = f2(ex2_approx(e0), ex2_approx(e1));
+  const F2 np = mul2(p, f2s(-1.0f));
+  const F2 erf_abs = fma2(np, e, f2s(1.0f));
+  const F2 hx = mul2(x, f2s(0.5f));
+  return fma2(abs2(hx), erf_abs, hx);
+}
+__device__ __forceinline__ ptx::F2 quick_gelu2(ptx::F2 x) {
+  using namespace ptx;
+  float a0, a1;
+  f2_get(mul2(x, f2s(-1.702f * 1.4426950408889634f)), a0, a1);
+  float d0, d1;
+  f2_get(add2(f2(ex2_approx(a0), ex2_approx(a1)), f2s(1.0f)), d0, d1);
+  return mul2(x, f2(rcp_approx(d0), rcp_approx(d1)));
+}
+template <int ACT>
+__device__ __forceinline__ ptx::F2 apply_act2(ptx::F2 x) {
+  if constexpr (ACT == ACT_GELU_ERF) return gelu_erf2(x);
+  else if constexpr (ACT == ACT_QUICK_GELU) return quick_gelu2(x);
+  else if constexpr (ACT == ACT_LEAKY) {
+    float a, b;
+    ptx::f2_get(x, a, b);
+    return ptx::f2(a > 0.f ? a : 0.01f * a, b > 0.f ? b : 0.01f * b);
+  } else return x;
 }
 
 template <int ACT>
@@ -150,30 +202,54 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
   }
 }
 
-// bias + activation on 32 accumulator columns
-template <int ACT>
-__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], float (&f)[32], const float* bias, int col) {
+// bias + activation on 32 accumulator columns, two columns per instruction; LNF: the folded LayerNorm first,
+//   f = rstd * acc + (-(mean * rstd) * s[col] + bias[col])
+template <int ACT, int LNF = 0>
+__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], float (&f)[32], const float* bias, int col,
+                                           const float* colsum = nullptr, float mean = 0.f, float rstd = 1.f) {
+  using namespace ptx;
+  const F2 r2 = f2s(rstd), nmr2 = f2s(-mean * rstd);
+  const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+  const float4* s4 = reinterpret_cast<const float4*>(colsum + col);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 8; ++j) {
+    F2 a0 = f2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]));
+    F2 a1 = f2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    if constexpr (LNF != 0) {
+      const float4 b = __ldg(b4 + j), s = __ldg(s4 + j);
+      a0 = fma2(r2, a0, fma2(nmr2, f2(s.x, s.y), f2(b.x, b.y)));
+      a1 = fma2(r2, a1, fma2(nmr2, f2(s.z, s.w), f2(b.z, b.w)));
+    } else if (bias != nullptr) {
       const float4 b = __ldg(b4 + j);
-      f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+      a0 = add2(a0, f2(b.x, b.y));
+      a1 = add2(a1, f2(b.z, b.w));
     }
+    a0 = apply_act2<ACT>(a0);
+    a1 = apply_act2<ACT>(a1);
+    f2_get(a0, f[4 * j + 0], f[4 * j + 1]);
+    f2_get(a1, f[4 * j + 2], f[4 * j + 3]);
   }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = apply_act<ACT>(f[j]);
 }
 
 // One epilogue warp drains its 32 rows x 128 accumulator columns: TMEM -> regs -> swizzled smem -> TMA.
 // `stage` is this warp's private 4 KB buffer; lane == row.  Lane 0 owns the bulk async-groups.
-template <int ACT, int OUT, typename ArriveFn>
+template <int ACT, int OUT, int LNF = 0, typename ArriveFn>
 __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage, const CUtensorMap* tmC, int row0,
                                                 int col0, uint32_t lane, const Args& a, ArriveFn&& release_tmem) {
   uint8_t* my_row = stage + lane * 128;
   const uint32_t sw = lane & 7u;
+  float mean = 0.f, rstd = 1.f;
+  if constexpr (LNF != 0) {   // this lane's row statistics from the producer's per-slice partial sums
+    const int row = min(row0 + int(lane), a.M - 1);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < a.ln_slices; ++i) {
+      const float2 p = __ldg(a.ln_part + size_t(row) * a.ln_slices + i);
+      s1 += p.x; s2 += p.y;
+    }
+    const float inv_n = 1.0f / float(a.ln_width);
+    mean = s1 * inv_n;
+    rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv_n), 0.f) + a.ln_eps);
+  }
   constexpr int COLS_PER_STORE = (OUT == OUT_BF16) ? 64 : 32;   // 128 B per row either way
   constexpr int N_STORES = 128 / COLS_PER_STORE;
 #pragma unroll 1
@@ -187,10 +263,10 @@ __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage,
       ptx::tmem_ld_wait();
       if (c == N_STORES - 1) release_tmem();
       float f[32];
-      bias_act32<ACT>(v0, f, a.bias, col);
+      bias_act32<ACT, LNF>(v0, f, a.bias, col, a.ln_colsum, mean, rstd);
 #pragma unroll
       for (int j = 0; j < 16; ++j) w[j] = ptx::pack_bf16x2(f[2 * j], f[2 * j + 1]);
-      bias_act32<ACT>(v1, f, a.bias, col + 32);
+      bias_act32<ACT, LNF>(v1, f, a.bias, col + 32, a.ln_colsum, mean, rstd);
 #pragma unroll
       for (int j = 0; j < 16; ++j) w[16 + j] = ptx::pack_bf16x2(f[2 * j], f[2 * j + 1]);
     } else {
@@ -199,7 +275,7 @@ __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage,
       ptx::tmem_ld_wait();
       if (c == N_STORES - 1) release_tmem();
       float f[32];
-      bias_act32<ACT>(v, f, a.bias, col);
+      bias_act32<ACT, LNF>(v, f, a.bias, col, a.ln_colsum, mean, rstd);
 #pragma unroll
       for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(f[j]);
     }
@@ -219,6 +295,79 @@ __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage,
       ptx::bulk_commit();
     }
   }
+}
+
+// OUT_F32_RESID_LN epilogue of one warp: 32 rows x 128 columns of  x_new = x_old + acc + bias  (lane == row).
+// x_old arrives by TMA load into X (4 KB, 128B-swizzled), is updated in place and leaves by TMA store; the bf16 copy
+// of x_new collects in Y (4 KB = 64 columns) and leaves every second chunk; the row's sum / sum of squares over the 128
+// columns go to part_out.  The next x_old chunk is requested as soon as the store has finished READING X (the tile's
+// x_old was prefetched into L2 one tile ahead, see the caller), so a chunk costs one L2 round trip.
+template <typename ArriveFn>
+__device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stage, uint64_t* xbar, uint32_t& xphase,
+                                                  const CUtensorMap* tmC, const CUtensorMap* tmD, int row0, int col0,
+                                                  uint32_t lane, const Args& a, ArriveFn&& release_tmem) {
+  uint8_t* X = stage;
+  uint8_t* Y = stage + 4096;
+  uint8_t* xrow = X + lane * 128;
+  uint8_t* yrow = Y + lane * 128;
+  const uint32_t sw = lane & 7u;
+  const bool active = row0 < a.M;   // warp-uniform
+  float sum = 0.f, ssq = 0.f;
+  if (lane == 0) {
+    ptx::bulk_wait_read<0>();        // the previous tile's stores have finished reading X and Y
+    if (active) {
+      ptx::mbar_arrive_expect_tx(xbar, 4096);
+      ptx::tma_load_2d(X, tmC, xbar, col0, row0);
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int col = col0 + c * 32;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
+    ptx::tmem_ld_wait();
+    if (c == 3) release_tmem();
+    float f[32];
+    bias_act32<ACT_NONE>(v, f, a.bias, col);
+    if (active) { ptx::mbar_wait(xbar, xphase); xphase ^= 1u; }   // x_old chunk c has landed (rows >= M: zero fill)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float o0, o1, o2, o3;
+      ptx::ld_shared_v4(xrow + ((uint32_t(q) ^ sw) << 4), o0, o1, o2, o3);
+      f[4 * q + 0] += o0; f[4 * q + 1] += o1; f[4 * q + 2] += o2; f[4 * q + 3] += o3;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { sum += f[j]; ssq = fmaf(f[j], f[j], ssq); }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      ptx::st_shared_v4(xrow + ((uint32_t(q) ^ sw) << 4), __float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                        __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+    // Y is free: at c == 0 by the wait above, at c == 2 by the wait that preceded this chunk's x_old request
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      ptx::st_shared_v4(yrow + ((uint32_t((c & 1) * 4 + q) ^ sw) << 4), ptx::pack_bf16x2(f[8 * q], f[8 * q + 1]),
+                        ptx::pack_bf16x2(f[8 * q + 2], f[8 * q + 3]), ptx::pack_bf16x2(f[8 * q + 4], f[8 * q + 5]),
+                        ptx::pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (active && col < a.N) {
+        ptx::tma_store_2d(tmC, X, col, row0);
+        if (c & 1) ptx::tma_store_2d(tmD, Y, col0 + (c >> 1) * 64, row0);
+      }
+      ptx::bulk_commit();
+      if (c < 3) {
+        ptx::bulk_wait_read<0>();    // X (and Y) have been read: X may take the next x_old chunk
+        if (active) {
+          ptx::mbar_arrive_expect_tx(xbar, 4096);
+          ptx::tma_load_2d(X, tmC, xbar, col + 32, row0);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  const int row = row0 + int(lane);
+  if (row < a.M) a.part_out[size_t(row) * (a.N >> 7) + (col0 >> 7)] = make_float2(sum, ssq);
 }
 
 // OUT_DOTS epilogue of one warp: 32 rows x 128 accumulator columns -> three partial sums per row (lane == row).
@@ -248,11 +397,11 @@ __device__ __forceinline__ void epilogue_dots(uint32_t t_addr, int row0, int col
   if (row < a.M) a.partials[size_t(row) * (a.dots_cols >> 7) + (col0 >> 7)] = make_float4(ss, d0, d1, 0.f);
 }
 
-template <int CG, int ACT, int OUT>
+template <int CG, int ACT, int OUT, int LNF = 0>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const Args args) {
-  using C = Cfg<CG>;
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const Args args) {
+  using C = Cfg<CG, OUT == OUT_F32_RESID_LN>;
   extern __shared__ uint8_t smem_raw[];
   // identical offset in both CTAs of a pair: the dynamic smem window starts at the same address
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -265,6 +414,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* xbar = tempty + 3;   // OUT_F32_RESID_LN: one x_old barrier per epilogue warp
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = ptx::lane_id();
@@ -285,6 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     if constexpr (OUT != OUT_F32_PATCH) ptx::prefetch_tmap(&tmC);
+    if constexpr (OUT == OUT_F32_RESID_LN) ptx::prefetch_tmap(&tmD);
   }
   if (warp == 9 && ptx::elect_one()) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -295,6 +446,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_init(&tfull[a], 1);                          // tcgen05.commit
       ptx::mbar_init(&tempty[a], CG * C::NUM_EPI_WARPS);     // one arrive per epilogue warp of the pair
     }
+    if constexpr (OUT == OUT_F32_RESID_LN)
+      for (int w = 0; w < C::NUM_EPI_WARPS; ++w) ptx::mbar_init(&xbar[w], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 10) {
@@ -366,9 +519,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t half = warp >> 2;         // which 128 accumulator columns
     uint8_t* stage = staging + warp * C::STAGING_BYTES;
     uint32_t it = 0;
+    [[maybe_unused]] uint32_t xphase = 0;
+    // OUT_F32_RESID_LN: pull this warp's 32 x 128 block of x_old of tile `t` into L2 (one tile ahead of its use)
+    [[maybe_unused]] auto prefetch_x = [&](int t) {
+      if (t >= num_tiles || lane != 0) return;
+      const int mb = t / tiles_n, nb = t - mb * tiles_n;
+      const int r0 = mb * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
+      if (r0 >= args.M) return;
+      for (int c = 0; c < 4; ++c) ptx::tma_prefetch_l2_2d(&tmC, nb * C::BN + int(half) * 128 + c * 32, r0);
+    };
+    if constexpr (OUT == OUT_F32_RESID_LN) prefetch_x(cluster_id);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      if constexpr (OUT == OUT_F32_RESID_LN) prefetch_x(tile + num_clusters);
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
       const int row0 = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
@@ -394,9 +558,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int col0 = n_blk * C::BN + int(half) * 128;
         if (col0 < args.dots_cols) epilogue_dots<ACT>(t_addr, row0, col0, lane, args, release_tmem);
         else epilogue_staged<ACT, OUT_F32>(t_addr, stage, &tmC, row0, col0, lane, args, release_tmem);
+      } else if constexpr (OUT == OUT_F32_RESID_LN) {
+        epilogue_resid_ln(t_addr, stage, &xbar[warp], xphase, &tmC, &tmD, row0, n_blk * C::BN + int(half) * 128, lane,
+                          args, release_tmem);
       } else {
-        epilogue_staged<ACT, OUT>(t_addr, stage, &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args,
-                                  release_tmem);
+        epilogue_staged<ACT, OUT, LNF>(t_addr, stage, &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args,
+                                       release_tmem);
       }
     }
     if constexpr (OUT != OUT_F32_PATCH) {

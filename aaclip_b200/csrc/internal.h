@@ -9,9 +9,15 @@ namespace k {
 // out = epilogue(A[M,K] . W[N,K]^T); A, W bf16 K-contiguous (pitches lda/ldw elements, multiples of 8).
 // act: gemm::Act, out_mode: gemm::Out, cta_group: 1 or 2.
 // out_mode OUT_DOTS: see gemm::Args (anchors [dots_cols,2], partials float4 [M][dots_cols/128]).
+// LnFold: the folded-LayerNorm schedule (gemm_sm100.cuh).  Producer (out_mode OUT_F32_RESID_LN): xb / ldxb / part_out.
+// Consumer (bf16 outputs): part_in [M][slices] float2, colsum [N], eps; A is the bf16 copy, W the gamma-folded weight.
+struct LnFold {
+  void* xb = nullptr; int ldxb = 0; void* part_out = nullptr;
+  const void* part_in = nullptr; int slices = 0; float eps = 1e-5f; const float* colsum = nullptr;
+};
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, void* out,
                 int ldo, int act, int out_mode, const float* pos, int P, int cta_group, cudaStream_t stream,
-                const float* anchors = nullptr, void* partials = nullptr, int dots_cols = 0);
+                const float* anchors = nullptr, void* partials = nullptr, int dots_cols = 0, const LnFold* ln = nullptr);
 
 // dots[l][r] = (d0, d1) / max(sqrt(ss), 1e-12) summed over the n_slices 128-column partials of row r, level l
 // partials: [n_levels][rows][n_slices] float4 (ss, d0, d1, -)
@@ -29,8 +35,16 @@ int launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s
 
 // AA-CLIP adapter mix (model/adapter.py:92-99): x <- w * a * ||x|| / ||a|| + (1-w) * x, row-wise over `width`.
 // Optionally fuses the next LayerNorm: if ln_gamma != null writes LN(x_new) as bf16 to ln_out.
+// Folded-LayerNorm schedule: xb_out (bf16 copy of the new x) + part_out ([rows][part_slices] float2, whole-row sums
+// in slice 0) instead of ln_out.
 int launch_adapter_mix(float* x, const float* a, float w, int rows, int width, const float* ln_gamma,
-                       const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream);
+                       const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream, void* xb_out = nullptr,
+                       void* part_out = nullptr, int part_slices = 0);
+// xb <- bf16(x), part[r] <- (sum, sum of squares) of row r in slice 0 (other slices zero)
+int launch_rowstats_cast(const float* x, int rows, int width, void* xb, void* part, int part_slices, cudaStream_t stream);
+// Wf = bf16(W o gamma), colsum[n] = sum_k Wf[n,k], bias_f = bias + W beta   (W fp32 [N,K])
+int launch_fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K, void* Wf,
+                          float* colsum, float* bias_f, cudaStream_t stream);
 
 // Row-wise L2 normalise (F.normalize, eps 1e-12) of s[rows, ld] columns [col0, col0+width).
 //   out_f32 / out_bf16: normalised rows [rows, width] (either may be null)

@@ -140,6 +140,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
 
 // smem -> global tile store / fp32 reduce-add through a tensor map (bulk async-group completion).
 // Elements outside the tensor's bounds are clipped by the TMA unit (ragged M / N tails need no predicate).
+// L2 prefetch of a tensor tile (no smem destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(const void* p, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(smem_u32(p)) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
@@ -320,6 +328,15 @@ __device__ __forceinline__ void fadd2(float& o0, float& o1, float a0, float a1, 
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(o0), "=f"(o1) : "l"(d));
 }
+// the same as a value type, for longer packed chains (GEMM epilogue): two fp32 lanes in one 64-bit register pair
+struct F2 { uint64_t v; };
+__device__ __forceinline__ F2 f2(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ F2 f2s(float c) { return f2(c, c); }
+__device__ __forceinline__ void f2_get(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 abs2(F2 a) { F2 r; r.v = a.v & 0x7fffffff7fffffffull; return r; }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }

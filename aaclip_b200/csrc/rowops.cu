@@ -40,6 +40,21 @@ __device__ __forceinline__ float row_sumsq(const float4 (&v)[VEC]) {
   return ptx::warp_sum(s);
 }
 
+// bf16 copy of the row + (sum, sum of squares) into slice 0 of the row's partial-sum record (other slices zeroed)
+template <int VEC>
+__device__ __forceinline__ void rowstats_store(const float4 (&v)[VEC], int lane, __nv_bfloat16* xb, float2* part,
+                                               int slices) {
+  const float s1 = row_sum<VEC>(v), s2 = row_sumsq<VEC>(v);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    uint2 w;
+    w.x = ptx::pack_bf16x2(v[i].x, v[i].y);
+    w.y = ptx::pack_bf16x2(v[i].z, v[i].w);
+    *reinterpret_cast<uint2*>(xb + (i * 32 + lane) * 4) = w;
+  }
+  if (lane < slices) part[lane] = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+}
+
 // y = (x - mean) * rstd * gamma + beta written as bf16 (8 B per lane-chunk) and/or fp32
 template <int VEC>
 __device__ __forceinline__ void layernorm_store(const float4 (&v)[VEC], int lane, int width, const float* gamma,
@@ -95,7 +110,8 @@ template <int VEC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 adapter_mix_kernel(float* __restrict__ x, const float* __restrict__ a, float w, int rows,
                    const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float eps,
-                   __nv_bfloat16* __restrict__ ln_out) {
+                   __nv_bfloat16* __restrict__ ln_out, __nv_bfloat16* __restrict__ xb_out, float2* __restrict__ part_out,
+                   int part_slices) {
   ptx::grid_dep_sync();
   constexpr int width = VEC * 128;
   const int lane = threadIdx.x & 31;
@@ -119,6 +135,50 @@ adapter_mix_kernel(float* __restrict__ x, const float* __restrict__ a, float w, 
   }
   if (ln_gamma != nullptr)
     layernorm_store<VEC>(xv, lane, width, ln_gamma, ln_beta, eps, ln_out + (size_t)r * width, nullptr);
+  if (xb_out != nullptr) rowstats_store<VEC>(xv, lane, xb_out + (size_t)r * width, part_out + (size_t)r * part_slices, part_slices);
+}
+
+// Folded-LayerNorm schedule: the bf16 copy of a fp32 row + its (sum, sum of squares) in the producer's partial layout
+// (whole-row sums in slice 0, zeros elsewhere).  Used where no residual GEMM produced them: after ln_pre.
+template <int VEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+rowstats_cast_kernel(const float* __restrict__ x, int rows, __nv_bfloat16* __restrict__ xb, float2* __restrict__ part,
+                     int part_slices) {
+  ptx::grid_dep_sync();
+  constexpr int width = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float4 v[VEC];
+  load_row<VEC>(x + (size_t)r * width, lane, v);
+  rowstats_store<VEC>(v, lane, xb + (size_t)r * width, part + (size_t)r * part_slices, part_slices);
+}
+
+// Fold LayerNorm's affine into the Linear that consumes it (one warp per output feature n):
+//   Wf[n,k] = bf16(W[n,k] * gamma[k]);  colsum[n] = sum_k float(Wf[n,k])  (of the ROUNDED weights: it must cancel what
+//   the tensor core sums);  bias_f[n] = b[n] + sum_k W[n,k] * beta[k]
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int N, int K, __nv_bfloat16* __restrict__ Wf,
+                      float* __restrict__ colsum, float* __restrict__ bias_f) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float s = 0.f, bb = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 w = ldg4(W + (size_t)n * K + k), g = ldg4(gamma + k), b = ldg4(beta + k);
+    const __nv_bfloat16 f0 = __float2bfloat16(w.x * g.x), f1 = __float2bfloat16(w.y * g.y),
+                        f2 = __float2bfloat16(w.z * g.z), f3 = __float2bfloat16(w.w * g.w);
+    s += (__bfloat162float(f0) + __bfloat162float(f1)) + (__bfloat162float(f2) + __bfloat162float(f3));
+    bb += (w.x * b.x + w.y * b.y) + (w.z * b.z + w.w * b.w);
+    uint2 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(f0) | ((uint32_t)__bfloat16_as_ushort(f1) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(f2) | ((uint32_t)__bfloat16_as_ushort(f3) << 16);
+    *reinterpret_cast<uint2*>(Wf + (size_t)n * K + k) = o;
+  }
+  s = ptx::warp_sum(s);
+  bb = ptx::warp_sum(bb);
+  if (lane == 0) { colsum[n] = s; bias_f[n] = (bias ? bias[n] : 0.f) + bb; }
 }
 
 // F.normalize(dim=-1, eps=1e-12) of s[r, col0:col0+width]; optionally also the two anchor dot products
@@ -302,12 +362,38 @@ int k::launch_layernorm(const float* x, const float* gamma, const float* beta, f
 }
 
 int k::launch_adapter_mix(float* x, const float* a, float w, int rows, int width, const float* ln_gamma,
-                          const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream) {
+                          const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream, void* xb_out,
+                          void* part_out, int part_slices) {
   if (rows <= 0) return host::OK;
   if (width % 128 != 0) return host::fail(host::ERR_INVALID, "adapter_mix: width %d must be a multiple of 128", width);
+  if (xb_out && (!part_out || part_slices < 1 || part_slices > 32))
+    return host::fail(host::ERR_INVALID, "adapter_mix: xb_out needs part_out and 1..32 slices");
   DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(adapter_mix_kernel<V>, dim3(row_blocks(rows)),
                                                      dim3(WARPS_PER_BLOCK * 32), 0, stream, x, a, w, rows, ln_gamma, ln_beta,
-                                                     eps, static_cast<__nv_bfloat16*>(ln_out_bf16))));
+                                                     eps, static_cast<__nv_bfloat16*>(ln_out_bf16),
+                                                     static_cast<__nv_bfloat16*>(xb_out), static_cast<float2*>(part_out),
+                                                     part_slices)));
+  return host::OK;
+}
+
+int k::launch_rowstats_cast(const float* x, int rows, int width, void* xb, void* part, int part_slices, cudaStream_t stream) {
+  if (rows <= 0) return host::OK;
+  if (width % 128 != 0 || part_slices < 1 || part_slices > 32)
+    return host::fail(host::ERR_INVALID, "rowstats_cast: width %d / slices %d", width, part_slices);
+  DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(rowstats_cast_kernel<V>, dim3(row_blocks(rows)),
+                                                     dim3(WARPS_PER_BLOCK * 32), 0, stream, x, rows,
+                                                     static_cast<__nv_bfloat16*>(xb), static_cast<float2*>(part),
+                                                     part_slices)));
+  return host::OK;
+}
+
+int k::launch_fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K, void* Wf,
+                             float* colsum, float* bias_f, cudaStream_t stream) {
+  if (N <= 0) return host::OK;
+  if (K % 4 != 0) return host::fail(host::ERR_INVALID, "fold_ln_weight: K=%d must be a multiple of 4", K);
+  fold_ln_weight_kernel<<<row_blocks(N), WARPS_PER_BLOCK * 32, 0, stream>>>(W, bias, gamma, beta, N, K,
+                                                                         static_cast<__nv_bfloat16*>(Wf), colsum, bias_f);
+  AACLIP_CUDA_CHECK(cudaGetLastError());
   return host::OK;
 }
 
@@ -377,4 +463,13 @@ extern "C" int aaclip_layernorm(const float* x, const float* gamma, const float*
 extern "C" int aaclip_adapter_mix(float* x, const float* a, float w, int rows, int width, void* stream) {
   return k::launch_adapter_mix(x, a, w, rows, width, nullptr, nullptr, 0.f, nullptr,
                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int aaclip_rowstats_cast(const float* x, int rows, int width, void* xb, void* part, int part_slices, void* stream) {
+  return k::launch_rowstats_cast(x, rows, width, xb, part, part_slices, static_cast<cudaStream_t>(stream));
+}
+extern "C" int aaclip_fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
+                                     void* Wf, float* colsum, float* bias_f, void* stream) {
+  if (!W || !gamma || !beta || !Wf || !colsum || !bias_f) return host::fail(host::ERR_INVALID, "fold_ln_weight: null argument");
+  return k::launch_fold_ln_weight(W, bias, gamma, beta, N, K, Wf, colsum, bias_f, static_cast<cudaStream_t>(stream));
 }

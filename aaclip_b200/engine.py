@@ -62,7 +62,7 @@ class Engine:
     """One context on one B200.  Not thread-safe (neither is the reference's nn.Module)."""
 
     def __init__(self, cfg: ModelCfg, device: int = 0, max_batch: int = 64, max_text: int = 16,
-                 text: bool = True, cta_group: int = 0):
+                 text: bool = True, cta_group: int = 0, ln_fold: Optional[bool] = None):
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device
@@ -82,6 +82,7 @@ class Engine:
                                                                         cfg.t_heads, cfg.t_layers)
             c.text_adapt_until, c.text_adapt_weight = cfg.text_adapt_until, cfg.text_adapt_weight
         c.max_batch, c.max_text, c.cta_group = max_batch, max_text, cta_group
+        c.ln_fold = 0 if ln_fold is None else (1 if ln_fold else 2)
         self._ctx = C.c_void_p()
         check(self.lib.aaclip_create(C.byref(self._ctx), C.byref(c), device))
         self._wmap = weight_map(cfg, self.has_text)

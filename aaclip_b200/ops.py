@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (ACT_GELU_ERF, ACT_LEAKY, ACT_NONE, ACT_QUICK_GELU, HEAD_TEST_INDUSTRIAL, HEAD_TEST_MEDICAL,
                    HEAD_TRAIN_SOFTMAX, OUT_BF16, OUT_F32, OUT_F32_PATCH, OUT_F32_RESID, check, cur_stream, ptr)
 
-__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head", "preprocess_u8", "resize_bicubic_u8", "map_minmax",
+__all__ = ["gemm", "layernorm", "attention", "adapter_mix", "anomaly_head", "preprocess_u8", "resize_bicubic_u8", "map_minmax", "gemm_resid_ln", "gemm_lnfold", "rowstats_cast", "fold_ln_weight",
            "ACT_NONE", "ACT_GELU_ERF", "ACT_QUICK_GELU", "ACT_LEAKY",
            "OUT_BF16", "OUT_F32", "OUT_F32_RESID", "OUT_F32_PATCH",
            "HEAD_TEST_INDUSTRIAL", "HEAD_TEST_MEDICAL", "HEAD_TRAIN_SOFTMAX"]
@@ -160,4 +160,51 @@ def map_minmax(maps: torch.Tensor) -> torch.Tensor:
     n_pix = maps.numel() // B if B else 0
     out = torch.empty(B, 2, device=maps.device, dtype=torch.float32)
     check(_lib.load().aaclip_map_minmax(ptr(maps), B, n_pix, ptr(out), cur_stream()))
+    return out
+
+
+# ---- folded-LayerNorm building blocks (see include/aaclip_b200.h) -------------------------------------------------
+def fold_ln_weight(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """W fp32 [N,K], LayerNorm affine (gamma, beta) -> (Wf bf16 [N,K], colsum fp32 [N], bias_f fp32 [N])."""
+    _need(w, torch.float32, "w"); _need(gamma, torch.float32, "gamma"); _need(beta, torch.float32, "beta")
+    N, K = w.shape
+    wf = torch.empty(N, K, device=w.device, dtype=torch.bfloat16)
+    colsum = torch.empty(N, device=w.device, dtype=torch.float32)
+    bias_f = torch.empty(N, device=w.device, dtype=torch.float32)
+    check(_lib.load().aaclip_fold_ln_weight(ptr(w), ptr(bias), ptr(gamma), ptr(beta), N, K, ptr(wf), ptr(colsum),
+                                            ptr(bias_f), cur_stream()))
+    return wf, colsum, bias_f
+
+
+def rowstats_cast(x: torch.Tensor, slices: int):
+    """x fp32 [rows,width] -> (bf16 copy, part fp32 [rows,slices,2] with the whole-row (sum, sum sq) in slice 0)."""
+    _need(x, torch.float32, "x")
+    rows, width = x.shape
+    xb = torch.empty(rows, width, device=x.device, dtype=torch.bfloat16)
+    part = torch.empty(rows, slices, 2, device=x.device, dtype=torch.float32)
+    check(_lib.load().aaclip_rowstats_cast(ptr(x), rows, width, ptr(xb), ptr(part), slices, cur_stream()))
+    return xb, part
+
+
+def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor, cta_group: int = 2):
+    """x += a @ w^T + bias in place (fp32); returns (bf16 copy of the new x, part fp32 [M, N/128, 2])."""
+    _need(a, torch.bfloat16, "a"); _need(w, torch.bfloat16, "w"); _need(x, torch.float32, "x")
+    M, K = a.shape
+    N = w.shape[0]
+    xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    part = torch.empty(M, N // 128, 2, device=a.device, dtype=torch.float32)
+    check(_lib.load().aaclip_gemm_resid_ln(ptr(a), K, ptr(w), K, M, N, K, ptr(bias), ptr(x), N, ptr(xb), N, ptr(part),
+                                           cta_group, cur_stream()))
+    return xb, part
+
+
+def gemm_lnfold(xb: torch.Tensor, wf: torch.Tensor, bias_f: torch.Tensor, colsum: torch.Tensor, part: torch.Tensor,
+                eps: float = 1e-5, act: int = ACT_NONE, cta_group: int = 2) -> torch.Tensor:
+    """bf16 [M,N] = act(LayerNorm(x) @ W^T + b) computed from the bf16 copy xb, the folded weight and the row statistics."""
+    _need(xb, torch.bfloat16, "xb"); _need(wf, torch.bfloat16, "wf"); _need(part, torch.float32, "part")
+    M, K = xb.shape
+    N = wf.shape[0]
+    out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
+    check(_lib.load().aaclip_gemm_lnfold(ptr(xb), K, ptr(wf), K, M, N, K, ptr(bias_f), ptr(colsum), ptr(part),
+                                         part.shape[1], eps, ptr(out), N, act, cta_group, cur_stream()))
     return out

@@ -106,6 +106,8 @@ typedef struct {
   int max_batch;    /* images per visual forward the workspaces are sized for */
   int max_text;     /* sentences per text forward */
   int cta_group;    /* 1 or 2: tcgen05 cta_group used by the GEMMs (0 = library default) */
+  int ln_fold;      /* visual tower: 0 = library default (on, AACLIP_LN_FOLD=0 turns it off), 1 = fold ln_1 / ln_2 into
+                       the in_proj / c_fc GEMMs (no LayerNorm launches inside the blocks), 2 = separate LayerNorm kernels */
 } aaclip_cfg;
 
 typedef struct aaclip_ctx aaclip_ctx;
@@ -205,6 +207,22 @@ int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int c
 /* out = epilogue(A[M,K] . W[N,K]^T), bf16 operands (pitches lda/ldw elements), fp32 accumulation. */
 int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                      void* out, int ldo, int act, int out_mode, const float* pos, int P, int cta_group, void* stream);
+/* The folded-LayerNorm schedule of the visual tower (LN(x) W^T + b == rstd (x (W o gamma)^T - mean s) + b'): the
+ * residual GEMM leaves the new fp32 rows, their bf16 copy and per-128-column (sum, sum of squares); the next GEMM
+ * consumes the bf16 copy and applies the row statistics in its epilogue - no LayerNorm kernel in between.
+ *   aaclip_gemm_resid_ln : x <- x + A W^T + bias (fp32 [M,N], in place), xb <- bf16(x), part[M][N/128] float2
+ *   aaclip_gemm_lnfold   : out bf16 [M,N] <- act(rstd_r (A Wf^T - mean_r colsum[n]) + bias[n]); statistics over K from
+ *                          part [M][slices]
+ *   aaclip_rowstats_cast : xb <- bf16(x), part[r][0] <- whole-row sums (other slices 0)
+ *   aaclip_fold_ln_weight: Wf = bf16(W o gamma) [N,K], colsum[n] = sum_k Wf[n,k], bias_f = bias + W beta */
+int aaclip_gemm_resid_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, float* x,
+                         int ldx, void* xb, int ldxb, void* part_out, int cta_group, void* stream);
+int aaclip_gemm_lnfold(const void* A, int lda, const void* Wf, int ldw, int M, int N, int K, const float* bias,
+                       const float* colsum, const void* part, int slices, float eps, void* out, int ldo, int act,
+                       int cta_group, void* stream);
+int aaclip_rowstats_cast(const float* x, int rows, int width, void* xb, void* part, int part_slices, void* stream);
+int aaclip_fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K, void* Wf,
+                          float* colsum, float* bias_f, void* stream);
 /* LayerNorm (model/transformer.py:37-43), fp32 in -> bf16 and/or fp32 out. */
 int aaclip_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
                      void* out_bf16, float* out_f32, void* stream);

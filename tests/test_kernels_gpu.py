@@ -199,3 +199,75 @@ def test_map_minmax(B, n):
         v.copy_(mm)
         g2 = ops.map_minmax(v)
         assert torch.equal(g2[:, 0], mm.amin(1)) and torch.equal(g2[:, 1], mm.amax(1))
+
+
+# ------------------------------------------------------------------------------------------------ folded LayerNorm
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("M,K", [(1154, 1024), (300, 4096)])
+def test_gemm_resid_ln(cg, M, K):
+    """Residual GEMM of the folded-LayerNorm schedule: x += A W^T + b through TMA load / store, bf16 copy, partial sums."""
+    ops = _ops()
+    N = 1024
+    a = _rand_bf16(M, K, seed=21)
+    w = _rand_bf16(N, K, scale=K ** -0.5, seed=22)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(23)).cuda()
+    x0 = (torch.randn(M, N, generator=torch.Generator().manual_seed(24)) * 3 + 0.5).cuda()
+    x = x0.clone()
+    xb, part = ops.gemm_resid_ln(a, w, bias, x, cta_group=cg)
+    torch.cuda.synchronize()
+    ref = x0 + a.float() @ w.float().t() + bias
+    _, rel = _report(f"gemm resid_ln cg{cg} K{K}", x, ref)
+    assert rel < 2e-3
+    assert torch.equal(xb, x.to(torch.bfloat16))                       # the bf16 copy is of the rows that were stored
+    sl = x.view(M, N // 128, 128)
+    assert (part[..., 0] - sl.sum(-1)).abs().max() < 2e-3 * 128
+    assert ((part[..., 1] - (sl * sl).sum(-1)).abs() / (sl * sl).sum(-1)).max() < 1e-5
+
+
+def test_fold_ln_weight_and_rowstats():
+    ops = _ops()
+    g = torch.Generator().manual_seed(31)
+    N, K = 768, 1024
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    gamma = (1 + 0.2 * torch.randn(K, generator=g)).cuda()
+    beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    wf, colsum, bias_f = ops.fold_ln_weight(w, b, gamma, beta)
+    assert torch.equal(wf, (w * gamma).to(torch.bfloat16))
+    assert (colsum - wf.float().sum(1)).abs().max() < 1e-4
+    assert (bias_f - (b + w @ beta)).abs().max() < 1e-4
+    x = (torch.randn(300, K, generator=g) * 2 + 1).cuda()
+    xb, part = ops.rowstats_cast(x, 8)
+    assert torch.equal(xb, x.to(torch.bfloat16))
+    assert (part[:, 0, 0] - x.sum(1)).abs().max() < 1e-2 and ((part[:, 0, 1] - (x * x).sum(1)).abs() / (x * x).sum(1)).max() < 1e-5
+    assert bool((part[:, 1:] == 0).all())
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("act", ["none", "gelu_erf"])
+@pytest.mark.parametrize("row_mean", [0.0, 2.0])
+def test_gemm_lnfold_vs_layernorm_linear(cg, act, row_mean):
+    """act(LayerNorm(x) W^T + b) from the bf16 copy of x + row statistics == the fp32 reference (LayerNorm then Linear)
+    within the tolerance of the unfolded bf16 path; a non-zero row mean exercises the mean * colsum cancellation."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(41)
+    M, K, N = 1154, 1024, 1024
+    x = (torch.randn(M, K, generator=g) * 1.7 + row_mean).cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    gamma = (1 + 0.2 * torch.randn(K, generator=g)).cuda()
+    beta = (0.1 * torch.randn(K, generator=g)).cuda()
+    wf, colsum, bias_f = ops.fold_ln_weight(w, b, gamma, beta)
+    xb, part = ops.rowstats_cast(x, 8)
+    code = {"none": ops.ACT_NONE, "gelu_erf": ops.ACT_GELU_ERF}[act]
+    out = ops.gemm_lnfold(xb, wf, bias_f, colsum, part, 1e-5, code, cta_group=cg)
+    torch.cuda.synchronize()
+    z = F.layer_norm(x, (K,), gamma, beta, 1e-5) @ w.t() + b
+    ref = z if act == "none" else F.gelu(z)
+    # the unfolded path on the same data, for scale: LN in fp32 -> bf16 -> GEMM with bf16 weights
+    xn, _ = ops.layernorm(x, gamma, beta)
+    base = ops.gemm(xn, w.to(torch.bfloat16), bias=b, act=code, out_mode=ops.OUT_BF16, cta_group=cg)
+    e_fold = (out.float() - ref).abs().max().item()
+    e_base = (base.float() - ref).abs().max().item()
+    print(f"[lnfold {act} cg{cg} mean{row_mean}] folded err {e_fold:.3e}  unfolded err {e_base:.3e}  ref absmax {ref.abs().max().item():.2f}")
+    assert e_fold < max(2.5 * e_base, 2e-3 * ref.abs().max().item() + 2 ** -7 * ref.abs().max().item())

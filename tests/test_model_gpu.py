@@ -394,3 +394,37 @@ def test_relu_projections_and_quick_gelu_vs_oracle(relu, quick_gelu):
         assert e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
     finally:
         eng.close()
+
+
+def test_ln_fold_and_separate_layernorm_schedules_agree():
+    """The two schedules of the visual tower - LayerNorm folded into the in_proj / c_fc GEMMs (default) and separate
+    LayerNorm kernels - are the same function up to bf16 rounding: both must sit inside the oracle tolerances and
+    within 2x the tolerance of each other; weights re-uploaded after creation must re-fold."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.VIT_L_14_336
+    sd, ia = synth.clip_state_dict(cfg, 0), synth.image_adapter_state_dict(cfg, 0)
+    img = synth.images(2, cfg, seed=77)
+    T = synth.anchors(cfg, seed=1)
+    with torch.no_grad():
+        seg_o, det_o = orc.visual_forward(sd, ia, img)
+        map_o, score_o = orc.predict(seg_o, det_o, T, cfg.image_size, "Industrial")
+    outs = {}
+    for fold in (True, False):
+        eng = Engine(cfg, device=0, max_batch=2, text=False, ln_fold=fold)
+        # first a DIFFERENT seed, then the real weights: the folded copies must follow the second upload
+        eng.load_state_dicts(synth.clip_state_dict(cfg, 5), synth.image_adapter_state_dict(cfg, 5), None)
+        eng.forward_fused(img.cuda(), T.cuda())
+        eng.load_state_dicts(sd, ia, None)
+        seg, det = eng.visual_forward(img.cuda())
+        maps, scores = eng.forward_fused(img.cuda(), T.cuda())
+        torch.cuda.synchronize()
+        outs[fold] = (torch.stack(seg).cpu(), det.cpu(), maps.cpu(), scores.cpu())
+        eng.close()
+        e_seg = (outs[fold][0] - torch.stack(seg_o)).abs().max().item()
+        e_map = (_mm(outs[fold][2]) - _mm(map_o)).abs().max().item()
+        print(f"[ln_fold={fold}] seg {e_seg:.3e} normalised map {e_map:.3e} score {(outs[fold][3] - score_o).abs().max().item():.3e}")
+        assert e_seg < SEG_TOL and e_map < MAP_NORM_TOL and (outs[fold][3] - score_o).abs().max() < SCORE_TOL
+    assert (outs[True][0] - outs[False][0]).abs().max() < 2 * SEG_TOL
+    assert (_mm(outs[True][2]) - _mm(outs[False][2])).abs().max() < 2 * MAP_NORM_TOL
