@@ -300,8 +300,9 @@ __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage,
 // OUT_F32_RESID_LN epilogue of one warp: 32 rows x 128 columns of  x_new = x_old + acc + bias  (lane == row).
 // x_old arrives by TMA load into X (4 KB, 128B-swizzled), is updated in place and leaves by TMA store; the bf16 copy
 // of x_new collects in Y (4 KB = 64 columns) and leaves every second chunk; the row's sum / sum of squares over the 128
-// columns go to part_out.  The next x_old chunk is requested as soon as the store has finished READING X (the tile's
-// x_old was prefetched into L2 one tile ahead, see the caller), so a chunk costs one L2 round trip.
+// columns go to part_out.  The next x_old chunk is requested as soon as the store has finished READING X.  (Pulling the
+// tile's x_old into L2 ahead of time - by these warps one tile ahead, or by the TMA producer late in the mainloop - was
+// measured 3-7 % SLOWER than no prefetch: out_proj 98.6 vs 102-105 us, c_proj 242 vs 249-253 us.)
 template <typename ArriveFn>
 __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stage, uint64_t* xbar, uint32_t& xphase,
                                                   const CUtensorMap* tmC, const CUtensorMap* tmD, int row0, int col0,
@@ -313,13 +314,7 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
   const uint32_t sw = lane & 7u;
   const bool active = row0 < a.M;   // warp-uniform
   float sum = 0.f, ssq = 0.f;
-  if (lane == 0) {
-    ptx::bulk_wait_read<0>();        // the previous tile's stores have finished reading X and Y
-    if (active) {
-      ptx::mbar_arrive_expect_tx(xbar, 4096);
-      ptx::tma_load_2d(X, tmC, xbar, col0, row0);
-    }
-  }
+  // (the caller requested x_old chunk 0 before it waited for the accumulator: resid_ln_request_first)
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int col = col0 + c * 32;
@@ -368,6 +363,18 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
   }
   const int row = row0 + int(lane);
   if (row < a.M) a.part_out[size_t(row) * (a.N >> 7) + (col0 >> 7)] = make_float2(sum, ssq);
+}
+
+// First x_old chunk of a tile, requested BEFORE the warp waits for the tile's accumulator (hides one round trip).
+__device__ __forceinline__ void resid_ln_request_first(uint8_t* stage, uint64_t* xbar, const CUtensorMap* tmC, int row0,
+                                                       int col0, uint32_t lane, const Args& a) {
+  if (lane == 0) {
+    ptx::bulk_wait_read<0>();        // the previous tile's stores have finished reading X and Y
+    if (row0 < a.M) {
+      ptx::mbar_arrive_expect_tx(xbar, 4096);
+      ptx::tma_load_2d(stage, tmC, xbar, col0, row0);
+    }
+  }
 }
 
 // OUT_DOTS epilogue of one warp: 32 rows x 128 accumulator columns -> three partial sums per row (lane == row).
@@ -520,22 +527,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* stage = staging + warp * C::STAGING_BYTES;
     uint32_t it = 0;
     [[maybe_unused]] uint32_t xphase = 0;
-    // OUT_F32_RESID_LN: pull this warp's 32 x 128 block of x_old of tile `t` into L2 (one tile ahead of its use)
-    [[maybe_unused]] auto prefetch_x = [&](int t) {
-      if (t >= num_tiles || lane != 0) return;
-      const int mb = t / tiles_n, nb = t - mb * tiles_n;
-      const int r0 = mb * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
-      if (r0 >= args.M) return;
-      for (int c = 0; c < 4; ++c) ptx::tma_prefetch_l2_2d(&tmC, nb * C::BN + int(half) * 128 + c * 32, r0);
-    };
-    if constexpr (OUT == OUT_F32_RESID_LN) prefetch_x(cluster_id);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
-      if constexpr (OUT == OUT_F32_RESID_LN) prefetch_x(tile + num_clusters);
+      const int row0 = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
+      if constexpr (OUT == OUT_F32_RESID_LN)
+        resid_ln_request_first(stage, &xbar[warp], &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args);
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
-      const int row0 = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * C::BN + half * 128u;
       // every TMEM read of this accumulator buffer is done: hand it back to the MMA warp
       auto release_tmem = [&]() {

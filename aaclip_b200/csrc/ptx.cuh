@@ -140,11 +140,6 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
 
 // smem -> global tile store / fp32 reduce-add through a tensor map (bulk async-group completion).
 // Elements outside the tensor's bounds are clipped by the TMA unit (ragged M / N tails need no predicate).
-// L2 prefetch of a tensor tile (no smem destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void ld_shared_v4(const void* p, float& a, float& b, float& c, float& d) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(smem_u32(p)) : "memory");
 }
