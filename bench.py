@@ -331,10 +331,12 @@ def main():
         "flop_per_launch_avg": gemm_flop_step / max(gemm_launches, 1), "launches_per_step": gemm_launches,
         "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / tot_ms,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of the two
-        # largest GEMMs (profiles/r1_ncu_gemm_full.txt): c_fc 331 MB (algorithmic 386 MB: part of the 302 MB bf16
-        # output is still in L2 when the kernel ends), c_proj 596 MB (algorithmic 613 MB incl. the fp32 residual RMW)
-        "traffic": (330.9e6 + 596.4e6) / 2, "traffic_detail": {"gemm_fc": 330.9e6, "gemm_proj": 596.4e6,
-                                                                "algorithmic": {"gemm_fc": 386.4e6, "gemm_proj": 613.3e6}},
+        # largest GEMMs (profiles/r1_ncu_full_summaries.txt, r1c_gemm_full): c_fc with folded ln_2 336 MB (algorithmic
+        # 386 MB: part of the 302 MB bf16 output is still in L2 when the kernel ends), c_proj with the residual +
+        # bf16-copy + statistics epilogue 703 MB (algorithmic 692 MB: h 302, W 8, x read 151 + write 151, bf16 copy 76,
+        # partial sums 2)
+        "traffic": (336.4e6 + 702.6e6) / 2, "traffic_detail": {"gemm_fc": 336.4e6, "gemm_proj": 702.6e6,
+                                                                "algorithmic": {"gemm_fc": 386.4e6, "gemm_proj": 691.5e6}},
         "achieved_in_timed_region_estimate": gemm_tflops * (span_ms / (ms / args.steps)),
         "whole_step_tflops": F_IMG * B / (ms / args.steps / 1e3) / 1e12,
         "whole_step_frac": F_IMG * B / (ms / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
