@@ -287,34 +287,45 @@ head_fused_kernel(SegPtrs seg, const float* __restrict__ anchors, const float* _
 #pragma unroll
     for (int j = 0; j < 8; ++j) tt[i][j] = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
   const int p_end = min(P, int(rank + 1) * chunk);
-  for (int p = int(rank) * chunk + warp; p < p_end; p += FUSED_THREADS / 32) {
-    const size_t row = (size_t)b * P + p;
-    uint4 raw[NL][CH];
+  // PP patches per warp and iteration: all PP * NL * CH 16-byte loads of a lane are in flight before the first use
+  // (memory-level parallelism is what bounds this phase: 6 KB per warp and patch)
+  constexpr int PP = 2, WARPS = FUSED_THREADS / 32;
+  for (int p0 = int(rank) * chunk + warp; p0 < p_end; p0 += WARPS * PP) {
+    uint4 raw[PP][NL][CH];
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(seg.p[l]) + row * E + lane * 8;
+    for (int u = 0; u < PP; ++u) {
+      const int p = min(p0 + u * WARPS, p_end - 1);   // a clamped duplicate is computed and dropped
+      const size_t row = (size_t)b * P + p;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) raw[l][i] = __ldcs(reinterpret_cast<const uint4*>(f + i * 256));
-    }
-    float acc = 0.f;
+      for (int l = 0; l < NL; ++l) {
+        const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(seg.p[l]) + row * E + lane * 8;
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[l][i]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 v = __bfloat1622float2(h[j]);
-          d0 += v.x * tt[i][2 * j].x + v.y * tt[i][2 * j + 1].x;
-          d1 += v.x * tt[i][2 * j].y + v.y * tt[i][2 * j + 1].y;
-        }
+        for (int i = 0; i < CH; ++i) raw[u][l][i] = __ldcs(reinterpret_cast<const uint4*>(f + i * 256));
       }
-      d0 = ptx::warp_sum(d0);
-      d1 = ptx::warp_sum(d1);
-      acc += (100.0f * d1 + 1.0f - 100.0f * d0) * 0.5f;   // per level exactly as the reference (test.py:85)
     }
-    if (lane == 0) m_part[p - int(rank) * chunk] = acc;
+#pragma unroll
+    for (int u = 0; u < PP; ++u) {
+      float acc = 0.f;
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][l][i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 v = __bfloat1622float2(h[j]);
+            d0 += v.x * tt[i][2 * j].x + v.y * tt[i][2 * j + 1].x;
+            d1 += v.x * tt[i][2 * j].y + v.y * tt[i][2 * j + 1].y;
+          }
+        }
+        d0 = ptx::warp_sum(d0);
+        d1 = ptx::warp_sum(d1);
+        acc += (100.0f * d1 + 1.0f - 100.0f * d0) * 0.5f;   // per level exactly as the reference (test.py:85)
+      }
+      const int p = p0 + u * WARPS;
+      if (lane == 0 && p < p_end) m_part[p - int(rank) * chunk] = acc;
+    }
   }
   // image score (test.py:83-84) by one warp of the cluster's first CTA
   if (rank == 0 && warp == 0 && scores != nullptr) {

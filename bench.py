@@ -439,23 +439,33 @@ def main():
     head = None
     try:
         from aaclip_b200 import ops
-        feats = [torch.nn.functional.normalize(torch.randn(B, cfg.patches, cfg.embed_dim, device="cuda"), dim=-1)
-                 .to(torch.bfloat16) for _ in range(4)]
-        det = torch.randn(B, cfg.embed_dim, device="cuda")
-        for _ in range(3):
-            ops.anomaly_head(feats, anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        h0.record()
-        for _ in range(reps):
-            ops.anomaly_head(feats, anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
-        h1.record()
-        torch.cuda.synchronize()
-        hms = h0.elapsed_time(h1) / reps
-        gbs = HEAD_BYTES_IMG * B / (hms / 1e3) / 1e9
+
+        def head_rate(hb):
+            # two rotating input sets of 4 levels: at hb = 64 one set is 226 MB, so every call streams from HBM
+            sets = [[torch.nn.functional.normalize(torch.randn(hb, cfg.patches, cfg.embed_dim, device="cuda"), dim=-1)
+                     .to(torch.bfloat16) for _ in range(4)] for _ in range(2)]
+            det = torch.randn(hb, cfg.embed_dim, device="cuda")
+            for i in range(3):
+                ops.anomaly_head(sets[i % 2], anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            h0.record()
+            for i in range(reps):
+                ops.anomaly_head(sets[i % 2], anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
+            h1.record()
+            torch.cuda.synchronize()
+            hms = h0.elapsed_time(h1) / reps
+            return hms, HEAD_BYTES_IMG * hb / (hms / 1e3) / 1e9
+
+        hms, gbs = head_rate(B)
+        hms4, gbs4 = head_rate(4 * B)
         head = {"bound": "hbm", "kernel": "head_fused_kernel (aaclip_anomaly_head: cluster of 8 CTAs per image, dots -> DSMEM gather -> blur -> bilinear -> map + score)", "achieved": gbs,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "ms": hms,
-                "images_per_s": B / (hms / 1e3), "note": "4 levels x 56.6 MB of bf16 tokens = 226 MB per call > 126 MB L2: repeats stream from HBM"}
+                "images_per_s": B / (hms / 1e3),
+                "note": "inputs alternate between two sets of 4 levels (2 x 226 MB at batch 64 > 126 MB L2): every call streams from HBM; "
+                        "at batch 64 the 64 clusters are a single wave, so the load phase and the blur / upsample / store phase do not overlap",
+                "at_4x_batch": {"batch": 4 * B, "ms": hms4, "achieved": gbs4, "frac": gbs4 / peaks["hbm_gbs"],
+                                "images_per_s": 4 * B / (hms4 / 1e3)}}
     except Exception as e:  # the head microbench must never sink the headline line
         head = {"error": str(e)}
 

@@ -271,3 +271,30 @@ def test_gemm_lnfold_vs_layernorm_linear(cg, act, row_mean):
     e_base = (base.float() - ref).abs().max().item()
     print(f"[lnfold {act} cg{cg} mean{row_mean}] folded err {e_fold:.3e}  unfolded err {e_base:.3e}  ref absmax {ref.abs().max().item():.2f}")
     assert e_fold < max(2.5 * e_base, 2e-3 * ref.abs().max().item() + 2 ** -7 * ref.abs().max().item())
+
+
+@pytest.mark.parametrize("env", [{"AACLIP_ATTN_BAL": "1"}, {"AACLIP_ATTN_DEEP": "1"}, {"AACLIP_ATTN_BAL": "1", "AACLIP_ATTN_DEEP": "1"},
+                                 {"AACLIP_ATTN_CTAS": "3"}], ids=["bal", "deep", "bal_deep", "ctas3"])
+def test_attention_diagnostic_variants(env):
+    """The attention variants kept behind environment switches (8-warp scheduler-balanced CTAs, three-tile S look-ahead,
+    3 CTAs / SM) are read once per process, so each runs in a child process; all must match the fp32 reference."""
+    import os, subprocess, sys
+    code = """
+import torch, math, sys
+sys.path.insert(0, %r)
+from aaclip_b200 import ops
+for (B, L, H, causal) in [(3, 577, 16, False), (2, 77, 12, True), (1, 1370, 16, False)]:
+    g = torch.Generator(device='cpu').manual_seed(B * 1000 + L)
+    qkv = (torch.randn(B * L, 3 * H * 64, generator=g) * 1.3).to(torch.bfloat16).cuda()
+    out = ops.attention(qkv, B, L, H, causal=causal).float().view(B, L, H, 64)
+    q, k, v = [t.view(B, L, H, 64).permute(0, 2, 1, 3) for t in qkv.float().view(B * L, 3, H * 64).unbind(1)]
+    s = q @ k.transpose(-1, -2) / 8
+    if causal: s = s + torch.full((L, L), float('-inf'), device='cuda').triu(1)
+    ref = (s.softmax(-1) @ v).permute(0, 2, 1, 3)
+    err = (out - ref).abs().max().item()
+    print(B, L, H, causal, err)
+    assert err < 2e-2, err
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0
