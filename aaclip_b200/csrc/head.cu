@@ -254,7 +254,7 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
 constexpr int FUSED_CLUSTER = 8;
 constexpr int FUSED_THREADS = 128;
 template <int NL>
-__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS)
+__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, 4)
 head_fused_kernel(SegPtrs seg, const float* __restrict__ anchors, const float* __restrict__ det, int P, int G, int S,
                   int mode, float* __restrict__ maps, float* __restrict__ scores) {
   ptx::grid_dep_sync();
@@ -281,11 +281,16 @@ head_fused_kernel(SegPtrs seg, const float* __restrict__ anchors, const float* _
     for (int i = 0; i < ksize; ++i) wk[i] /= sum;
   }
   // ---- phase 1: anchor dots of this CTA's patches
-  float2 tt[CH][8];
+  // the test-mode map needs only (s1 - s0) per level: ((100 d1) + 1 - (100 d0)) / 2 = 50 <f, T1 - T0> + 0.5, so a lane
+  // keeps the 24 DIFFERENCES of its anchor pairs (half the registers and FMAs of two separate dot products)
+  float td[CH][8];
 #pragma unroll
   for (int i = 0; i < CH; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tt[i][j] = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
+    for (int j = 0; j < 8; ++j) {
+      const float2 t2 = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
+      td[i][j] = t2.y - t2.x;
+    }
   const int p_end = min(P, int(rank + 1) * chunk);
   // PP patches per warp and iteration: all PP * NL * CH 16-byte loads of a lane are in flight before the first use
   // (memory-level parallelism is what bounds this phase: 6 KB per warp and patch)
@@ -308,20 +313,18 @@ head_fused_kernel(SegPtrs seg, const float* __restrict__ anchors, const float* _
       float acc = 0.f;
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
-        float d0 = 0.f, d1 = 0.f;
+        float d = 0.f;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][l][i]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 v = __bfloat1622float2(h[j]);
-            d0 += v.x * tt[i][2 * j].x + v.y * tt[i][2 * j + 1].x;
-            d1 += v.x * tt[i][2 * j].y + v.y * tt[i][2 * j + 1].y;
+            d = fmaf(v.x, td[i][2 * j], fmaf(v.y, td[i][2 * j + 1], d));
           }
         }
-        d0 = ptx::warp_sum(d0);
-        d1 = ptx::warp_sum(d1);
-        acc += (100.0f * d1 + 1.0f - 100.0f * d0) * 0.5f;   // per level exactly as the reference (test.py:85)
+        d = ptx::warp_sum(d);
+        acc += fmaf(50.0f, d, 0.5f);   // (s1 + 1 - s0) / 2 of this level (test.py:85)
       }
       const int p = p0 + u * WARPS;
       if (lane == 0 && p < p_end) m_part[p - int(rank) * chunk] = acc;
