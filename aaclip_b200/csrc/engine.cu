@@ -277,10 +277,11 @@ int run_block_fold(aaclip_ctx* c, const Tower& t, int i, int B, int L, float ada
   RUN(PC_GEMM_PROJ, k::launch_gemm(c->h, ff, l.proj_w, ff, rows, w, ff, l.proj_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID_LN,
                      nullptr, 0, cg, st, nullptr, nullptr, 0, &prod));
   if (i < (int)t.adapters.size()) {
-    RUN(PC_GEMM_ADAPTER, k::launch_gemm(c->xn, w, t.adapters[i], w, rows, w, w, nullptr, c->a, w, gemm::ACT_LEAKY, gemm::OUT_F32,
+    // the branch a is kept in bf16: it enters x with weight adapt_w = 0.1, a tenth of the rounding xb itself carries
+    RUN(PC_GEMM_ADAPTER, k::launch_gemm(c->xn, w, t.adapters[i], w, rows, w, w, nullptr, c->a, w, gemm::ACT_LEAKY, gemm::OUT_BF16,
                        nullptr, 0, cg, st));
     RUN(PC_ADAPTER_MIX, k::launch_adapter_mix(c->x, c->a, adapt_w, rows, w, nullptr, nullptr, 1e-5f, nullptr, st, c->xn, c->part,
-                              slices));
+                              slices, true));
   }
   return host::OK;
 }

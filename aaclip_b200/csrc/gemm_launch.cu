@@ -61,6 +61,7 @@ int dispatch(int act, int out_mode, const CUtensorMap& tmA, const CUtensorMap& t
   CASE(ACT_NONE, OUT_F32_RESID_LN)
   CASE(ACT_NONE, OUT_F32)
   CASE(ACT_LEAKY, OUT_F32)
+  CASE(ACT_LEAKY, OUT_BF16)
   CASE(ACT_NONE, OUT_F32_PATCH)
   CASE(ACT_NONE, OUT_DOTS)
   CASE(ACT_LEAKY, OUT_DOTS)

@@ -37,9 +37,9 @@ int launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_t s
 // Optionally fuses the next LayerNorm: if ln_gamma != null writes LN(x_new) as bf16 to ln_out.
 // Folded-LayerNorm schedule: xb_out (bf16 copy of the new x) + part_out ([rows][part_slices] float2, whole-row sums
 // in slice 0) instead of ln_out.
-int launch_adapter_mix(float* x, const float* a, float w, int rows, int width, const float* ln_gamma,
+int launch_adapter_mix(float* x, const void* a, float w, int rows, int width, const float* ln_gamma,
                        const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream, void* xb_out = nullptr,
-                       void* part_out = nullptr, int part_slices = 0);
+                       void* part_out = nullptr, int part_slices = 0, bool a_is_bf16 = false);
 // xb <- bf16(x), part[r] <- (sum, sum of squares) of row r in slice 0 (other slices zero)
 int launch_rowstats_cast(const float* x, int rows, int width, void* xb, void* part, int part_slices, cudaStream_t stream);
 // Wf = bf16(W o gamma), colsum[n] = sum_k Wf[n,k], bias_f = bias + W beta   (W fp32 [N,K])

@@ -106,9 +106,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                        out_f32 ? out_f32 + (size_t)r * width : nullptr);
 }
 
-template <int VEC>
+template <int VEC, bool A_BF16>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-adapter_mix_kernel(float* __restrict__ x, const float* __restrict__ a, float w, int rows,
+adapter_mix_kernel(float* __restrict__ x, const void* __restrict__ a_, float w, int rows,
                    const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, float eps,
                    __nv_bfloat16* __restrict__ ln_out, __nv_bfloat16* __restrict__ xb_out, float2* __restrict__ part_out,
                    int part_slices) {
@@ -120,7 +120,18 @@ adapter_mix_kernel(float* __restrict__ x, const float* __restrict__ a, float w, 
   float* xr = x + (size_t)r * width;
   float4 xv[VEC], av[VEC];
   load_row<VEC>(xr, lane, xv);
-  load_row<VEC>(a + (size_t)r * width, lane, av);
+  if constexpr (A_BF16) {   // the folded schedule keeps the adapter branch in bf16 (it enters x with weight w = 0.1)
+    const __nv_bfloat16* ar = static_cast<const __nv_bfloat16*>(a_) + (size_t)r * width;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const uint2 q = __ldcs(reinterpret_cast<const uint2*>(ar + (i * 32 + lane) * 4));
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+      av[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+  } else {
+    load_row<VEC>(static_cast<const float*>(a_) + (size_t)r * width, lane, av);
+  }
   const float nx = sqrtf(row_sumsq<VEC>(xv));
   const float na = sqrtf(row_sumsq<VEC>(av));
   const float sa = w * (nx / na);  // no epsilon, as in the reference (model/adapter.py:94-98)
@@ -290,29 +301,43 @@ dots_finish_kernel(const float4* __restrict__ partials, long long total_rows, in
   dots[r] = make_float2(d0 * inv, d1 * inv);
 }
 
-// image fp32 [B,3,S,S] -> A bf16 [B*G*G, Kpad]; k = c*ps*ps + i*ps + j (conv1.weight.view(width,-1) order)
-__global__ void im2col_kernel(const float* __restrict__ img, int B, int S, int ps, int G, int Kpad,
-                              __nv_bfloat16* __restrict__ out) {
+// image fp32 [B,3,S,S] -> A bf16 [B*G*G, Kpad]; k = c*ps*ps + i*ps + j (conv1.weight.view(width,-1) order), zero padded.
+// One CTA per (image, patch row): the 3 x ps image rows it needs (3*ps*S floats, 56 KB at 336 px) are staged in shared
+// memory with coalesced 16-byte loads, a k -> smem-offset table replaces the per-element divisions, and every warp store
+// is 128 contiguous bytes of one output row.
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ img, int S, int ps, int G, int Kpad, __nv_bfloat16* __restrict__ out) {
   ptx::grid_dep_sync();
-  const long long total = (long long)B * G * G * (Kpad / 2);
-  const int K = 3 * ps * ps;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int kp = int(t % (Kpad / 2));
-    const long long m = t / (Kpad / 2);
-    const int gx = int(m % G), gy = int((m / G) % G), b = int(m / ((long long)G * G));
-    float v[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int k = kp * 2 + e;
-      float val = 0.f;
-      if (k < K) {
-        const int c = k / (ps * ps), rem = k - c * ps * ps, i = rem / ps, j = rem - i * ps;
-        val = __ldg(img + (((long long)b * 3 + c) * S + (gy * ps + i)) * S + gx * ps + j);
-      }
-      v[e] = val;
+  extern __shared__ float im_sm[];          // [3][ps][S] floats, then Kpad ints
+  const int K = 3 * ps * ps, band = ps * S;
+  int* off = reinterpret_cast<int*>(im_sm + 3 * band);
+  const int gy = blockIdx.x % G, b = blockIdx.x / G;
+  for (int c = 0; c < 3; ++c) {
+    const float* src = img + (((long long)b * 3 + c) * S + (long long)gy * ps) * S;   // ps consecutive rows: contiguous
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(band * sizeof(float))) & 15u) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(im_sm + c * band);
+      for (int i = threadIdx.x; i < band / 4; i += blockDim.x) d4[i] = __ldcs(s4 + i);
+    } else {
+      for (int i = threadIdx.x; i < band; i += blockDim.x) im_sm[c * band + i] = __ldcs(src + i);
     }
-    *reinterpret_cast<uint32_t*>(out + m * Kpad + kp * 2) = ptx::pack_bf16x2(v[0], v[1]);
+  }
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int o = -1;
+    if (k < K) {
+      const int c = k / (ps * ps), rem = k - c * ps * ps, i = rem / ps, j = rem - i * ps;
+      o = c * band + i * S + j;
+    }
+    off[k] = o;
+  }
+  __syncthreads();
+  const int kp_n = Kpad / 2;
+  __nv_bfloat16* dst = out + ((long long)b * G * G + (long long)gy * G) * Kpad;
+  for (int t = threadIdx.x; t < G * kp_n; t += blockDim.x) {
+    const int gx = t / kp_n, kp = t - gx * kp_n;
+    const int o0 = off[2 * kp], o1 = off[2 * kp + 1];
+    const float v0 = o0 >= 0 ? im_sm[o0 + gx * ps] : 0.f, v1 = o1 >= 0 ? im_sm[o1 + gx * ps] : 0.f;
+    *reinterpret_cast<uint32_t*>(dst + (long long)gx * Kpad + 2 * kp) = ptx::pack_bf16x2(v0, v1);
   }
 }
 
@@ -361,18 +386,26 @@ int k::launch_layernorm(const float* x, const float* gamma, const float* beta, f
   return host::OK;
 }
 
-int k::launch_adapter_mix(float* x, const float* a, float w, int rows, int width, const float* ln_gamma,
+int k::launch_adapter_mix(float* x, const void* a, float w, int rows, int width, const float* ln_gamma,
                           const float* ln_beta, float eps, void* ln_out_bf16, cudaStream_t stream, void* xb_out,
-                          void* part_out, int part_slices) {
+                          void* part_out, int part_slices, bool a_is_bf16) {
   if (rows <= 0) return host::OK;
   if (width % 128 != 0) return host::fail(host::ERR_INVALID, "adapter_mix: width %d must be a multiple of 128", width);
   if (xb_out && (!part_out || part_slices < 1 || part_slices > 32))
     return host::fail(host::ERR_INVALID, "adapter_mix: xb_out needs part_out and 1..32 slices");
-  DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(adapter_mix_kernel<V>, dim3(row_blocks(rows)),
-                                                     dim3(WARPS_PER_BLOCK * 32), 0, stream, x, a, w, rows, ln_gamma, ln_beta,
-                                                     eps, static_cast<__nv_bfloat16*>(ln_out_bf16),
-                                                     static_cast<__nv_bfloat16*>(xb_out), static_cast<float2*>(part_out),
-                                                     part_slices)));
+  if (a_is_bf16) {
+    DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(adapter_mix_kernel<V, true>, dim3(row_blocks(rows)),
+                                                       dim3(WARPS_PER_BLOCK * 32), 0, stream, x, a, w, rows, ln_gamma, ln_beta,
+                                                       eps, static_cast<__nv_bfloat16*>(ln_out_bf16),
+                                                       static_cast<__nv_bfloat16*>(xb_out), static_cast<float2*>(part_out),
+                                                       part_slices)));
+  } else {
+    DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(adapter_mix_kernel<V, false>, dim3(row_blocks(rows)),
+                                                       dim3(WARPS_PER_BLOCK * 32), 0, stream, x, a, w, rows, ln_gamma, ln_beta,
+                                                       eps, static_cast<__nv_bfloat16*>(ln_out_bf16),
+                                                       static_cast<__nv_bfloat16*>(xb_out), static_cast<float2*>(part_out),
+                                                       part_slices)));
+  }
   return host::OK;
 }
 
@@ -433,9 +466,12 @@ int k::launch_im2col(const float* image, int B, int S, int ps, int Kpad, void* o
   if (S % ps != 0 || Kpad % 8 != 0 || Kpad < 3 * ps * ps)
     return host::fail(host::ERR_INVALID, "im2col: S=%d ps=%d Kpad=%d", S, ps, Kpad);
   const int G = S / ps;
-  const long long total = (long long)B * G * G * (Kpad / 2);
-  const int blocks = int(std::min<long long>((total + 255) / 256, 148LL * 32));
-  AACLIP_CUDA_CHECK(host::launch(im2col_kernel, dim3(blocks), dim3(256), 0, stream, image, B, S, ps, G, Kpad,
+  if (B <= 0) return host::OK;
+  const size_t smem = (size_t)3 * ps * S * sizeof(float) + (size_t)Kpad * sizeof(int);
+  if (smem > 220 * 1024) return host::fail(host::ERR_INVALID, "im2col: %zu B of shared memory (S=%d ps=%d)", smem, S, ps);
+  if (smem > 48 * 1024)
+    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AACLIP_CUDA_CHECK(host::launch(im2col_kernel, dim3(B * G), dim3(256), smem, stream, image, S, ps, G, Kpad,
                                  static_cast<__nv_bfloat16*>(out_bf16)));
   return host::OK;
 }
