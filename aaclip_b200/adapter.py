@@ -169,6 +169,7 @@ class AdaptedCLIP(nn.Module):
     def predict_stream(self, batches, text_feature: torch.Tensor, domain: str = "Industrial"):
         """The batch loop of test.py:get_predictions (test.py:60-99) over an iterable of CPU image batches, pipelined
         (upload of batch k+1 and download of batch k-1 overlap the compute of batch k).  Yields
-        (maps [B,S,S], scores [B]) as pinned CPU tensors, in order.  Batches must not exceed `max_batch`."""
+        (maps [B,S,S], scores [B]) as pinned CPU tensors, in order.  Batches are float32 [B,3,S,S] or raw uint8
+        [B,H0,W0,3] (the loader's transform_x then runs on the device); larger ones than `max_batch` go in chunks."""
         eng = self._sync_engine(next(self.parameters()).device)
         yield from eng.predict_stream(batches, text_feature, domain)

@@ -226,10 +226,17 @@ class Engine:
         while batch k computes, batch k+1 uploads and batch k-1 downloads.  Yields (maps [B,S,S], scores [B]) as
         pinned CPU tensors, in order.  A batch is either float32 [B,3,S,S] (already transformed, as the reference's
         DataLoader delivers it) or uint8 [B,H0,W0,3] raw RGB, in which case the loader's transform_x
-        (dataset/__init__.py:127-136) also runs on the device."""
+        (dataset/__init__.py:127-136) also runs on the device.  Batches larger than `max_batch` are split into chunks."""
         S = self.cfg.image_size
         anchors = anchors.detach().float().cpu().contiguous()
-        pending = []
+        inflight = []   # tickets in submission order: (ticket, batch record); at most two
+        ready = []      # batch records in input order: {"left": chunks not yet landed, "out": (maps, scores), "keep": ...}
+
+        def drain_one():
+            t, rec = inflight.pop(0)
+            self.wait_host(t)
+            rec["left"] -= 1
+
         for img in batches:
             img = img.detach()
             raw = img.dtype == torch.uint8   # [B,H0,W0,3] undecoded-size RGB bytes: transform_x runs on the device
@@ -240,17 +247,26 @@ class Engine:
                 img = img.float().cpu().contiguous()
             if not img.is_pinned():
                 img = img.pin_memory()
-            maps = torch.empty(img.shape[0], S, S).pin_memory()
-            scores = torch.empty(img.shape[0]).pin_memory()
-            if len(pending) == 2:
-                t, keep = pending.pop(0)
-                self.wait_host(t)
-                yield keep[1], keep[2]
+            n = img.shape[0]
+            maps = torch.empty(n, S, S).pin_memory()
+            scores = torch.empty(n).pin_memory()
+            rec = {"left": 0, "out": (maps, scores), "keep": img}
+            ready.append(rec)
             submit = self.submit_host_u8 if raw else self.submit_host
-            pending.append((submit(img, anchors, maps, scores, domain), (img, maps, scores)))
-        for t, keep in pending:
-            self.wait_host(t)
-            yield keep[1], keep[2]
+            for b0 in range(0, n, self.max_batch):   # a batch larger than max_batch rides the two slots in chunks
+                b1 = min(n, b0 + self.max_batch)
+                if len(inflight) == 2:
+                    drain_one()
+                inflight.append((submit(img[b0:b1], anchors, maps[b0:b1], scores[b0:b1], domain), rec))
+                rec["left"] += 1
+            while ready and ready[0]["left"] == 0 and all(r is not ready[0] for _, r in inflight):
+                yield ready.pop(0)["out"]
+        while inflight:
+            drain_one()
+            while ready and ready[0]["left"] == 0 and all(r is not ready[0] for _, r in inflight):
+                yield ready.pop(0)["out"]
+        for rec in ready:   # empty batches
+            yield rec["out"]
 
     def text_forward(self, tokens: torch.Tensor) -> torch.Tensor:
         """AdaptedCLIP.encode_text(adapt_text=True): int32 [n, ctx] -> fp32 [n, t_width]."""

@@ -138,6 +138,19 @@ def test_host_pipeline_matches_device_entry(full):
     assert len(got) == len(ref)
     for (m, s), (mr, sr) in zip(got, ref):
         assert torch.equal(m, mr) and torch.equal(s, sr)
+    # batches larger than max_batch (6 and 9 > 4) are split into chunks; an empty batch passes through
+    big = [torch.cat([batches[0], batches[4]]), torch.cat([batches[3], batches[2], batches[4]]), batches[1][:0], batches[1]]
+    got = list(eng.predict_stream(big, T))
+    want = [(torch.cat([ref[0][0], ref[4][0]]), torch.cat([ref[0][1], ref[4][1]])),
+            (torch.cat([ref[3][0], ref[2][0], ref[4][0]]), torch.cat([ref[3][1], ref[2][1], ref[4][1]])),
+            (ref[1][0][:0], ref[1][1][:0]), ref[1]]
+    assert len(got) == 4
+    for (m, s), (mr, sr) in zip(got, want):
+        assert m.shape == mr.shape and s.shape == sr.shape
+    # chunk boundaries differ from the reference batches only where the composition differs: results are per image
+    assert torch.equal(got[0][0], want[0][0]) and torch.equal(got[0][1], want[0][1])
+    assert torch.equal(got[3][0], want[3][0])
+    assert (got[1][0] - want[1][0]).abs().max() < 1e-5 and torch.equal(got[1][0][:4], want[1][0][:4])
     # a third submit without a wait is refused (two slots), then the pipeline drains normally
     bufs = [(b.pin_memory(), torch.empty(b.shape[0], 336, 336).pin_memory(), torch.empty(b.shape[0]).pin_memory())
             for b in batches[:3]]
