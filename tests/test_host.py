@@ -171,3 +171,34 @@ def test_image_level_preds_matches_metrics_eval_restatement():
     ex1 = np.stack([maps1.min(axis=(1, 2)), maps1.max(axis=(1, 2))], 1)
     _, want = orc.metrics_image_preds(maps1, scores, "Industrial")
     assert np.array_equal(fu.image_level_preds(ex1, scores, "Industrial"), want.astype(np.float32))
+
+
+def test_new_entry_points_argument_checks_without_gpu():
+    """Host-side validation of the loader-transform / extrema / folded-GEMM entry points: pure arithmetic helpers and
+    the argument errors that are raised before any CUDA call (no compute without a GPU)."""
+    import ctypes as C
+    from aaclip_b200 import _lib
+    lib = _lib.load()
+    # scratch = uint8 result of the horizontal pass, [B, H0, S, 3]; none when the width does not change
+    assert lib.aaclip_preprocess_scratch_bytes(64, 1024, 1024, 336) == 64 * 1024 * 336 * 3
+    assert lib.aaclip_preprocess_scratch_bytes(2, 500, 336, 336) == 0
+    assert lib.aaclip_preprocess_scratch_bytes(0, 10, 10, 5) == 0
+    # empty batches are a no-op, null pointers / bad sizes are AACLIP_ERR_INVALID with a message
+    assert lib.aaclip_preprocess_u8(None, 0, 8, 8, 4, None, None, None, None, None) == 0
+    assert lib.aaclip_map_minmax(None, 0, 16, None, None) == 0
+    assert lib.aaclip_preprocess_u8(None, 1, 8, 8, 4, None, None, None, None, None) == -1
+    assert b"null" in lib.aaclip_last_error()
+    buf = (C.c_uint8 * 16)()
+    out = (C.c_float * 16)()
+    assert lib.aaclip_preprocess_u8(buf, 1, 0, 8, 4, None, None, None, out, None) == -1      # H0 = 0
+    assert lib.aaclip_preprocess_u8(buf, 1, 8, 20000, 4, None, None, buf, out, None) == -1  # row too wide for smem
+    assert b"too wide" in lib.aaclip_last_error()
+    assert lib.aaclip_preprocess_u8(buf, 1, 8, 8, 4, None, None, None, out, None) == -1      # scratch missing
+    assert b"scratch" in lib.aaclip_last_error()
+    assert lib.aaclip_map_minmax(None, 2, 16, None, None) == -1
+    assert lib.aaclip_fold_ln_weight(None, None, None, None, 8, 8, None, None, None, None) == -1
+    # folded-GEMM building blocks: shape rules are checked before the device is touched
+    assert lib.aaclip_gemm_resid_ln(buf, 64, buf, 64, 128, 384, 64, None, out, 384, buf, 384, out, 2, None) == -1
+    assert b"256" in lib.aaclip_last_error()                                                 # N % 256 != 0
+    assert lib.aaclip_gemm_lnfold(buf, 64, buf, 64, 128, 256, 64, None, None, out, 8, 1e-5, buf, 256, 0, 2, None) == -1
+    assert b"colsum" in lib.aaclip_last_error()
