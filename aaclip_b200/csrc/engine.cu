@@ -298,14 +298,17 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
   RUN(PC_GEMM_PATCH, k::launch_gemm(c->col, c->Kpad, c->conv_w, c->Kpad, prow, w, c->Kpad, nullptr, c->x, w, gemm::ACT_NONE,
                      gemm::OUT_F32_PATCH, c->pos, P, cg, st));
   RUN(PC_STEM_MISC, k::launch_cls_rows(c->x, c->cls, c->pos, B, L, w, st));
-  RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, nullptr, c->x, st));
-  bool xn_ready = false;
-  int level = 0;
   const bool fold = c->ln_fold;
   if (fold) {
+    // ln_pre also leaves the bf16 copy of its output and the row sums the first in_proj epilogue needs
     TRY(refold(c, st));
-    RUN(PC_CAST, k::launch_rowstats_cast(c->x, rows, w, c->xn, c->part, w / 128, st));
+    RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, c->xn, c->x, st, c->part,
+                            w / 128));
+  } else {
+    RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_pre_g, c->ln_pre_b, 1e-5f, rows, w, 0, 0, 0, nullptr, c->x, st));
   }
+  bool xn_ready = false;
+  int level = 0;
   for (int i = 0; i < cfg.layers; ++i) {
     if (fold) TRY(run_block_fold(c, c->v, i, B, L, cfg.image_adapt_weight, st));
     else TRY(run_block(c, c->v, i, B, L, 0, cfg.image_adapt_weight, &xn_ready, st));

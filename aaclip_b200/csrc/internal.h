@@ -28,7 +28,9 @@ int launch_dots_finish(const void* partials, int n_levels, int rows, int n_slice
 //   (lets ln_post skip the CLS row of every image without a copy).  out_bf16 and/or out_f32 may be null.
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
                      int rows_per_group, int row_offset, long long group_stride, void* out_bf16, float* out_f32,
-                     cudaStream_t stream);
+                     cudaStream_t stream, void* part_out = nullptr, int part_slices = 0);
+//   part_out ([rows][part_slices] float2): (sum, sum of squares) of every OUTPUT row in slice 0, zeros elsewhere - with
+//   out_bf16 this is what the folded-LayerNorm schedule needs from ln_pre.
 
 // fp32 -> bf16 cast of a [rows, width] matrix.
 int launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_t stream);

@@ -59,8 +59,9 @@ __device__ __forceinline__ void rowstats_store(const float4 (&v)[VEC], int lane,
 template <int VEC>
 __device__ __forceinline__ void layernorm_store(const float4 (&v)[VEC], int lane, int width, const float* gamma,
                                                 const float* beta, float eps, __nv_bfloat16* out_bf16,
-                                                float* out_f32) {
+                                                float* out_f32, float2* part_out = nullptr, int part_slices = 0) {
   const float inv_w = 1.0f / float(width);
+  float o1 = 0.f, o2 = 0.f;   // sum / sum of squares of the OUTPUT row (folded-LayerNorm schedule, after ln_pre)
   const float mean = row_sum<VEC>(v) * inv_w;
   float ss = 0.f;
 #pragma unroll
@@ -85,6 +86,13 @@ __device__ __forceinline__ void layernorm_store(const float4 (&v)[VEC], int lane
       *reinterpret_cast<uint2*>(out_bf16 + col) = w;
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + col) = y;
+    o1 += (y.x + y.y) + (y.z + y.w);
+    o2 += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+  }
+  if (part_out != nullptr) {
+    o1 = ptx::warp_sum(o1);
+    o2 = ptx::warp_sum(o2);
+    if (lane < part_slices) part_out[lane] = lane == 0 ? make_float2(o1, o2) : make_float2(0.f, 0.f);
   }
 }
 
@@ -92,7 +100,8 @@ template <int VEC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  float eps, int rows, int rows_per_group, int row_offset, long long group_stride,
-                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+                 __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, float2* __restrict__ part_out,
+                 int part_slices) {
   ptx::grid_dep_sync();
   constexpr int width = VEC * 128;
   const int lane = threadIdx.x & 31;
@@ -103,7 +112,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   float4 v[VEC];
   load_row<VEC>(src, lane, v);
   layernorm_store<VEC>(v, lane, width, gamma, beta, eps, out_bf16 ? out_bf16 + (size_t)r * width : nullptr,
-                       out_f32 ? out_f32 + (size_t)r * width : nullptr);
+                       out_f32 ? out_f32 + (size_t)r * width : nullptr,
+                       part_out ? part_out + (size_t)r * part_slices : nullptr, part_slices);
 }
 
 template <int VEC, bool A_BF16>
@@ -376,13 +386,15 @@ inline int row_blocks(int rows) { return (rows + WARPS_PER_BLOCK - 1) / WARPS_PE
 
 int k::launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
                         int rows_per_group, int row_offset, long long group_stride, void* out_bf16, float* out_f32,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, void* part_out, int part_slices) {
   if (rows <= 0) return host::OK;
   if (width % 128 != 0) return host::fail(host::ERR_INVALID, "layernorm: width %d must be a multiple of 128", width);
+  if (part_out && (part_slices < 1 || part_slices > 32)) return host::fail(host::ERR_INVALID, "layernorm: %d slices", part_slices);
   if (rows_per_group <= 0) { rows_per_group = rows; row_offset = 0; group_stride = 0; }
   DISPATCH_VEC(width, AACLIP_CUDA_CHECK(host::launch(layernorm_kernel<V>, dim3(row_blocks(rows)), dim3(WARPS_PER_BLOCK * 32),
                                                      0, stream, x, gamma, beta, eps, rows, rows_per_group, row_offset,
-                                                     group_stride, static_cast<__nv_bfloat16*>(out_bf16), out_f32)));
+                                                     group_stride, static_cast<__nv_bfloat16*>(out_bf16), out_f32,
+                                                     static_cast<float2*>(part_out), part_slices)));
   return host::OK;
 }
 
