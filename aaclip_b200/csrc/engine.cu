@@ -114,6 +114,19 @@ struct aaclip_ctx {
   // LayerNorm folded into the consumer GEMMs of the visual tower (see gemm_sm100.cuh); AACLIP_LN_FOLD=0 disables it
   bool ln_fold = true, fold_dirty = true;
   float2* part = nullptr;   // [rows][width / 128] (sum, sum of squares) per 128-column slice of the fp32 rows
+  // CUDA graphs of the fused forward (aaclip_forward_fused), one per (batch, pointers, mode): the ~100 launches of a
+  // chunk become one graph launch.  A key is run eagerly the first time, captured the second, replayed from then on.
+  struct FusedKey {
+    const float* image; const float* anchors; float* maps; float* scores; int B; int mode;
+    bool operator==(const FusedKey& o) const {
+      return image == o.image && anchors == o.anchors && maps == o.maps && scores == o.scores && B == o.B && mode == o.mode;
+    }
+  };
+  struct FusedGraph { FusedKey key; cudaGraphExec_t exec; long long launches; unsigned long long last_use; };
+  std::vector<FusedGraph> graphs;
+  std::vector<FusedKey> seen_once;
+  unsigned long long graph_clock = 0;
+  bool use_graphs = true;
   long long bytes = 0;
   long long launches = 0;
   std::vector<void*> allocs;
@@ -406,6 +419,7 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
   c->ln_fold = cfg->ln_fold == 1 ? true : cfg->ln_fold == 2 ? false
                : (getenv("AACLIP_LN_FOLD") ? atoi(getenv("AACLIP_LN_FOLD")) != 0 : true);
   if (w % 256 != 0 || w / 128 > 32) c->ln_fold = false;
+  c->use_graphs = getenv("AACLIP_GRAPH") ? atoi(getenv("AACLIP_GRAPH")) != 0 : true;
   if (c->ln_fold) {
     const long long ffv = cfg->mlp_width;
     for (auto& l : c->v.lw) {
@@ -446,6 +460,7 @@ extern "C" void aaclip_destroy(aaclip_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : c->allocs) cudaFree(p);
   for (auto& sl : c->slots) { if (sl.raw) cudaFree(sl.raw); if (sl.raw_scratch) cudaFree(sl.raw_scratch); }
   if (c->stage) cudaFree(c->stage);
@@ -608,6 +623,76 @@ extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, f
   return host::OK;
 }
 
+namespace {
+// one chunk (<= max_batch images) of the fused forward, enqueued kernel by kernel
+int fused_chunk(aaclip_ctx* c, const float* image, int nb, const float* anchors, int mode, float* maps, float* scores,
+                cudaStream_t st) {
+  const int S = c->cfg.image_size;
+  TRY(visual_chunk(c, image, nb, nullptr, 0, c->det, anchors, c->dots, st));
+  if (maps) { RUN(PC_HEAD_MAPS, k::launch_head_maps(c->dots, nb, c->G, S, mode, c->cfg.n_levels, maps, st)); }
+  if (scores) { RUN(PC_OTHER, k::launch_scores(c->det, anchors, 0, nb, c->E, scores, st)); }
+  return host::OK;
+}
+
+// The same chunk through a CUDA graph when its key repeats (see aaclip_ctx::FusedGraph).  Not on the legacy default
+// stream (capture is not allowed there) and not while per-launch profiling is on.
+int fused_chunk_graphed(aaclip_ctx* c, const float* image, int nb, const float* anchors, int mode, float* maps,
+                        float* scores, cudaStream_t st) {
+  const bool eligible = c->use_graphs && !c->prof_on && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (!eligible) return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+  TRY(refold(c, st));   // never inside a capture: it runs only when weights changed
+  const aaclip_ctx::FusedKey key{image, anchors, maps, scores, nb, mode};
+  ++c->graph_clock;
+  for (auto& g : c->graphs)
+    if (g.key == key) {
+      g.last_use = c->graph_clock;
+      AACLIP_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+      c->launches += g.launches;
+      return host::OK;
+    }
+  bool seen = false;
+  for (auto& k2 : c->seen_once) seen = seen || (k2 == key);
+  if (!seen) {   // first sight: run eagerly (this also performs every one-time cudaFuncSetAttribute)
+    if (c->seen_once.size() >= 64) c->seen_once.erase(c->seen_once.begin());
+    c->seen_once.push_back(key);
+    return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+  }
+  // second sight: capture, instantiate, launch
+  const long long before = c->launches;
+  AACLIP_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  const long long n_launches = c->launches - before;
+  c->launches = before;
+  if (rc != host::OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    c->use_graphs = false;   // something on the path is not capturable here: stay eager from now on
+    if (rc != host::OK) return rc;
+    return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    c->use_graphs = false;
+    return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+  }
+  if (c->graphs.size() >= 16) {   // evict the least recently used
+    size_t v = 0;
+    for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].last_use < c->graphs[v].last_use) v = i;
+    cudaGraphExecDestroy(c->graphs[v].exec);
+    c->graphs.erase(c->graphs.begin() + v);
+  }
+  c->graphs.push_back({key, exec, n_launches, c->graph_clock});
+  AACLIP_CUDA_CHECK(cudaGraphLaunch(exec, st));
+  c->launches += n_launches;
+  return host::OK;
+}
+}  // namespace
+
 extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, const float* anchors, int mode,
                                     float* maps_out, float* scores_out, void* stream_) {
   TRY(check_ready(c));
@@ -621,11 +706,8 @@ extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, co
   const long long img_elems = 3LL * S * S;
   for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
     const int nb = std::min(c->cfg.max_batch, B - b0);
-    TRY(visual_chunk(c, image + b0 * img_elems, nb, nullptr, 0, c->det, anchors, c->dots, st));
-    if (maps_out) {
-      RUN(PC_HEAD_MAPS, k::launch_head_maps(c->dots, nb, c->G, S, mode, c->cfg.n_levels, maps_out + (long long)b0 * S * S, st));
-    }
-    if (scores_out) { RUN(PC_OTHER, k::launch_scores(c->det, anchors, 0, nb, c->E, scores_out + b0, st)); }
+    TRY(fused_chunk_graphed(c, image + b0 * img_elems, nb, anchors, mode,
+                            maps_out ? maps_out + (long long)b0 * S * S : nullptr, scores_out ? scores_out + b0 : nullptr, st));
   }
   return host::OK;
 }

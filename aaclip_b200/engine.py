@@ -166,14 +166,26 @@ class Engine:
         return seg, det
 
     def forward_fused(self, image: torch.Tensor, anchors: torch.Tensor, domain: str = "Industrial",
-                      want_maps: bool = True, want_scores: bool = True):
-        """image -> (level-summed anomaly maps fp32 [B,S,S], image scores fp32 [B]) without seg tokens."""
+                      want_maps: bool = True, want_scores: bool = True, out=None):
+        """image -> (level-summed anomaly maps fp32 [B,S,S], image scores fp32 [B]) without seg tokens.
+
+        `out = (maps, scores)` reuses caller-owned output tensors.  On a non-default stream a call whose pointers
+        (image, anchors, outputs) and batch repeat is replayed as ONE CUDA graph launch (captured at its second
+        occurrence), so steady-state loops should reuse their buffers."""
         self._check_image(image)
         if tuple(anchors.shape) != (self.cfg.embed_dim, 2) or anchors.dtype != torch.float32 or not anchors.is_cuda:
             raise ValueError("anchors must be a float32 CUDA tensor [E,2]")
         B, S = image.shape[0], self.cfg.image_size
-        maps = torch.empty(B, S, S, device=image.device, dtype=torch.float32) if want_maps else None
-        scores = torch.empty(B, device=image.device, dtype=torch.float32) if want_scores else None
+        if out is not None:
+            maps, scores = out
+            if maps is not None and (tuple(maps.shape) != (B, S, S) or maps.dtype != torch.float32 or not maps.is_cuda
+                                     or not maps.is_contiguous()):
+                raise ValueError(f"out maps must be a contiguous float32 CUDA tensor [{B},{S},{S}]")
+            if scores is not None and (tuple(scores.shape) != (B,) or scores.dtype != torch.float32 or not scores.is_cuda):
+                raise ValueError(f"out scores must be a float32 CUDA tensor [{B}]")
+        else:
+            maps = torch.empty(B, S, S, device=image.device, dtype=torch.float32) if want_maps else None
+            scores = torch.empty(B, device=image.device, dtype=torch.float32) if want_scores else None
         check(self.lib.aaclip_forward_fused(self._ctx, ptr(image), B, ptr(anchors.contiguous()), DOMAIN_MODE[domain],
                                             ptr(maps), ptr(scores), cur_stream()))
         return maps, scores

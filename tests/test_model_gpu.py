@@ -441,3 +441,39 @@ def test_ln_fold_and_separate_layernorm_schedules_agree():
         assert e_seg < SEG_TOL and e_map < MAP_NORM_TOL and (outs[fold][3] - score_o).abs().max() < SCORE_TOL
     assert (outs[True][0] - outs[False][0]).abs().max() < 2 * SEG_TOL
     assert (_mm(outs[True][2]) - _mm(outs[False][2])).abs().max() < 2 * MAP_NORM_TOL
+
+
+def test_cuda_graph_replay_is_bit_identical_and_follows_weight_updates(full):
+    """On a non-default stream a repeated (batch, pointers) call is captured into a CUDA graph at its second occurrence
+    and replayed afterwards: replays must be bit-identical to the eager launches, keep counting launches, and pick up
+    re-uploaded weights (the graph reads the same weight buffers; the fold kernels run outside it)."""
+    from aaclip_b200 import synth
+    cfg, eng, sd, ia, ta = full
+    T = synth.anchors(cfg, seed=1).cuda()
+    img = synth.images(3, cfg, seed=91).cuda()
+    eager = eng.forward_fused(img, T)                       # default stream: always eager
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    out = (torch.empty(3, 336, 336, device="cuda"), torch.empty(3, device="cuda"))
+    counts = []
+    with torch.cuda.stream(side):
+        for _ in range(5):                                   # eager, capture + launch, replay x3
+            n0 = eng.launch_count
+            eng.forward_fused(img, T, out=out)
+            side.synchronize()
+            counts.append(eng.launch_count - n0)
+            assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
+        assert len(set(counts)) == 1 and counts[0] > 50      # a replay counts the kernels of the graph
+        # different weights through the same buffers: the replayed graph must compute with them
+        eng.load_state_dicts(synth.clip_state_dict(cfg, 3), synth.image_adapter_state_dict(cfg, 3), None)
+        eng.forward_fused(img, T, out=out)
+        side.synchronize()
+        changed = out[0].clone()
+    eager2 = eng.forward_fused(img, T)
+    torch.cuda.synchronize()
+    assert torch.equal(changed, eager2[0]) and not torch.equal(changed, eager[0])
+    eng.load_state_dicts(sd, ia, None)                       # restore for the other tests of the module
+    with torch.cuda.stream(side):
+        eng.forward_fused(img, T, out=out)
+        side.synchronize()
+    assert torch.equal(out[0], eager[0])
