@@ -87,3 +87,18 @@ def test_gaussian_kernel_properties():
         assert abs(float(w.sum()) - 1) < 1e-6 and torch.equal(w, w.flip(0)) and int(w.argmax()) == k // 2
     x = torch.full((1, 1, 24, 24), 3.25)
     assert (orc.gaussian_blur2d(x, (7, 7), (1.0, 1.0)) - 3.25).abs().max() < 1e-6  # constants are preserved
+
+
+def test_gaussian_blur_against_independent_implementation():
+    """kornia==0.6.9 is absent offline, so its gaussian_blur2d stays "parity unpinned" - but the restated algorithm
+    (normalised exp(-x^2 / 2 sigma^2) window of k taps, reflect padding without edge repeat, separable) is exactly what
+    scipy.ndimage.gaussian_filter(mode="mirror", radius=k//2) computes: an independent cross-check of the restatement
+    for both operating points of forward_utils.py:205-210."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    import numpy as np
+    x = torch.randn(3, 1, 24, 24, generator=torch.Generator().manual_seed(5))
+    for k, s in ((7, 1.0), (9, 1.5)):
+        got = orc.gaussian_blur2d(x, (k, k), (s, s)).numpy()
+        want = np.stack([ndi.gaussian_filter(x[i, 0].numpy().astype(np.float64), sigma=s, radius=k // 2, mode="mirror")
+                         for i in range(3)])[:, None]
+        assert np.abs(got - want).max() < 2e-6
