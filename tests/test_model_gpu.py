@@ -477,3 +477,35 @@ def test_cuda_graph_replay_is_bit_identical_and_follows_weight_updates(full):
         eng.forward_fused(img, T, out=out)
         side.synchronize()
     assert torch.equal(out[0], eager[0])
+
+
+@pytest.mark.parametrize("offset", [3.0, -8.0])
+def test_ln_fold_with_large_row_mean_vs_oracle(offset):
+    """Stress for the folded LayerNorm: a large ln_pre bias gives every row of the residual stream a mean several times
+    its spread, the case in which rstd * (x W'^T - mean * colsum) cancels two big terms.  Both schedules must stay inside
+    the oracle tolerances (4-layer ViT-L-width model)."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.ModelCfg(layers=4, t_layers=0, image_adapt_until=2, levels=[1, 2, 3, 4])
+    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    sd = dict(sd)
+    sd["visual.ln_pre.bias"] = sd["visual.ln_pre.bias"] + offset
+    img, T = synth.images(2, cfg, seed=13), synth.anchors(cfg, seed=1)
+    with torch.no_grad():
+        seg_o, det_o = orc.visual_forward(sd, ia, img, layers=4, image_adapt_until=2, levels=(1, 2, 3, 4))
+        map_o, score_o = orc.predict(seg_o, det_o, T, cfg.image_size, "Industrial")
+    for fold in (True, False):
+        eng = Engine(cfg, device=0, max_batch=2, text=False, ln_fold=fold)
+        try:
+            eng.load_state_dicts(sd, ia, None)
+            seg, det = eng.visual_forward(img.cuda())
+            maps, scores = eng.forward_fused(img.cuda(), T.cuda())
+            torch.cuda.synchronize()
+            e_seg = max((a.cpu() - b).abs().max().item() for a, b in zip(seg, seg_o))
+            e_map = (_mm(maps.cpu()) - _mm(map_o)).abs().max().item()
+            e_sc = (scores.cpu() - score_o).abs().max().item()
+            print(f"[row mean {offset:+.0f}, ln_fold={fold}] seg {e_seg:.3e} normalised map {e_map:.3e} score {e_sc:.3e}")
+            assert e_seg <= SEG_TOL and e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
+        finally:
+            eng.close()
