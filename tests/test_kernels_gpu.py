@@ -298,3 +298,35 @@ for (B, L, H, causal) in [(3, 577, 16, False), (2, 77, 12, True), (1, 1370, 16, 
     r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0
+
+
+@pytest.mark.parametrize("pattern", ["late_spike", "rising", "huge", "tiny"])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_stabiliser_paths(pattern, causal):
+    """Score patterns that force the stale-stabiliser machinery of the softmax: the row maximum sits in the LAST key
+    (ragged tile, general path), grows tile after tile (repeated restabilisation + O rescale), is huge (exp2 arguments
+    far below -126 for the other keys) or every score is tiny.  fp32 softmax(QK^T/8)V is the reference."""
+    ops = _ops()
+    B, L, H = 2, 577 if not causal else 77, 4
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(B, L, H, 64, generator=g)
+    k = torch.randn(B, L, H, 64, generator=g)
+    v = torch.randn(B, L, H, 64, generator=g)
+    if pattern == "late_spike":      # every query loves the last key (and, causally, its own position)
+        k[:, -1] = 6.0 * q.mean(1)
+        q = q + 2.0 * q.mean(1, keepdim=True)
+    elif pattern == "rising":        # key norm grows along the sequence: the running max keeps increasing
+        k = k * torch.linspace(0.2, 6.0, L).view(1, L, 1, 1)
+        q = q.abs()
+        k = k.abs()
+    elif pattern == "huge":
+        q, k = q * 6.0, k * 6.0
+    else:
+        q, k = q * 1e-3, k * 1e-3
+    qkv = torch.stack([q, k, v], 2).reshape(B * L, 3 * H * 64).to(torch.bfloat16).cuda()
+    out = ops.attention(qkv, B, L, H, causal)
+    torch.cuda.synchronize()
+    ref = _attention_ref(qkv, B, L, H, causal)
+    err, rel = _report(f"attn {pattern} causal={causal}", out, ref)
+    assert not torch.isnan(out.float()).any() and not torch.isinf(out.float()).any()
+    assert rel < 1.5e-2
