@@ -57,17 +57,18 @@ SIGNATURES = {
     "aaclip_profile_enable": (_i, [_vp, _i]),
     "aaclip_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_ll), _i]),
     "aaclip_profile_span_ms": (C.c_double, [_vp]),
-    "aaclip_visual_forward": (_i, [_vp, _vp, _i, C.POINTER(_vp), _vp, _vp]),
-    "aaclip_anomaly_head": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "aaclip_visual_forward": (_i, [_vp, _vp, _i, C.POINTER(_vp), _i, _vp, _vp]),
+    "aaclip_anomaly_head_workspace_bytes": (_ll, [_i, _i, _i]),
+    "aaclip_anomaly_head": (_i, [C.POINTER(_vp), _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
     "aaclip_map_minmax": (_i, [_vp, _i, _ll, _vp, _vp]),
-    "aaclip_forward_fused": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
-    "aaclip_forward_fused_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
-    "aaclip_submit_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, C.POINTER(_ll)]),
+    "aaclip_forward_fused": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "aaclip_forward_fused_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "aaclip_submit_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, C.POINTER(_ll)]),
     "aaclip_wait_host": (_i, [_vp, _ll]),
     "aaclip_preprocess_scratch_bytes": (_ll, [_i, _i, _i, _i]),
     "aaclip_preprocess_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "aaclip_resize_bicubic_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "aaclip_submit_host_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, C.POINTER(_ll)]),
+    "aaclip_submit_host_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, C.POINTER(_ll)]),
     "aaclip_text_forward": (_i, [_vp, _vp, _i, _vp, _vp]),
     "aaclip_text_anchor": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "aaclip_gemm_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
@@ -118,7 +119,9 @@ def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
-def cur_stream() -> int:
+def cur_stream(device=None) -> int:
+    """Raw handle of torch's current stream ON `device` (a tensor's or an engine's device, not the thread's current
+    one: a stream handle is only valid on the device it was created on)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

@@ -66,6 +66,7 @@ class AdaptedCLIP(nn.Module):
         levels: list = [6, 12, 18, 24],
         relu: bool = True,
         max_batch: int = 64,
+        seg_dtype: torch.dtype = torch.float32,
         **kwargs,
     ):
         super().__init__()
@@ -78,6 +79,8 @@ class AdaptedCLIP(nn.Module):
         self.levels = levels
         self.relu = relu
         self.max_batch = max_batch
+        # dtype of the patch tokens forward() returns: float32 as the reference; bfloat16 halves what the head streams
+        self.seg_dtype = seg_dtype
         width = clip_model.visual.conv1.out_channels
         t_width = clip_model.token_embedding.weight.shape[1] if hasattr(clip_model, "token_embedding") else 768
 
@@ -118,11 +121,14 @@ class AdaptedCLIP(nn.Module):
                                "move the model and its inputs to a cuda device")
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         if self._engine is None or self._engine.device != dev_index:
-            levels = sorted(int(l) for l in self.levels)
+            # the reference taps block i when `i + 1 in self.levels` (model/adapter.py:100): membership semantics, so
+            # duplicates fire once, order is irrelevant and a level outside [1, layers] never fires
+            levels = sorted({int(l) for l in self.levels})
             cfg = _infer_cfg(self.clipmodel, levels, self.image_adapt_until, self.text_adapt_until, self.i_w,
                              self.t_w, self.relu)
-            # as in the reference, a level outside [1, layers] simply never fires (model/adapter.py:100)
             cfg.levels = [l for l in levels if 1 <= l <= cfg.layers]
+            if not cfg.levels:
+                raise ValueError(f"no level of {list(self.levels)} lies in [1, {cfg.layers}]: nothing to tap")
             self._engine = Engine(cfg, device=dev_index, max_batch=self.max_batch)
             self._versions = {}
         eng = self._engine
@@ -147,7 +153,7 @@ class AdaptedCLIP(nn.Module):
     def forward(self, x: torch.Tensor):
         """model/adapter.py:67-112 -> (seg_tokens: list of [B,P,768] L2-normalised, det_token [B,768])."""
         eng = self._sync_engine(x.device)
-        seg, det = eng.visual_forward(x.float().contiguous())
+        seg, det = eng.visual_forward(x.float().contiguous(), seg_dtype=self.seg_dtype)
         return seg, det
 
     @torch.no_grad()
@@ -159,17 +165,21 @@ class AdaptedCLIP(nn.Module):
         return eng.text_forward(text)
 
     @torch.no_grad()
-    def predict(self, image: torch.Tensor, text_feature: torch.Tensor, domain: str = "Industrial"):
+    def predict(self, image: torch.Tensor, text_feature: torch.Tensor, domain: str = "Industrial",
+                with_extrema: bool = False):
         """Fused body of test.py:get_predictions for one batch (test.py:80-93): returns
-        (anomaly maps [B,S,S] = sum over levels of calculate_similarity_map(test=True), image scores [B])."""
+        (anomaly maps [B,S,S] = sum over levels of calculate_similarity_map(test=True), image scores [B]) and, with
+        `with_extrema`, the per-image (min, max) [B,2] of the maps (forward_utils.py:241-252) from the same kernel."""
         eng = self._sync_engine(image.device)
-        return eng.forward_fused(image.float().contiguous(), text_feature.float().contiguous(), domain)
+        ext = torch.empty(image.shape[0], 2, device=image.device, dtype=torch.float32) if with_extrema else None
+        maps, scores = eng.forward_fused(image.float().contiguous(), text_feature.float().contiguous(), domain, extrema=ext)
+        return (maps, scores, ext) if with_extrema else (maps, scores)
 
     @torch.no_grad()
-    def predict_stream(self, batches, text_feature: torch.Tensor, domain: str = "Industrial"):
+    def predict_stream(self, batches, text_feature: torch.Tensor, domain: str = "Industrial", with_extrema: bool = False):
         """The batch loop of test.py:get_predictions (test.py:60-99) over an iterable of CPU image batches, pipelined
         (upload of batch k+1 and download of batch k-1 overlap the compute of batch k).  Yields
         (maps [B,S,S], scores [B]) as pinned CPU tensors, in order.  Batches are float32 [B,3,S,S] or raw uint8
         [B,H0,W0,3] (the loader's transform_x then runs on the device); larger ones than `max_batch` go in chunks."""
         eng = self._sync_engine(next(self.parameters()).device)
-        yield from eng.predict_stream(batches, text_feature, domain)
+        yield from eng.predict_stream(batches, text_feature, domain, with_extrema=with_extrema)

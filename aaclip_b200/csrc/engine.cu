@@ -117,9 +117,10 @@ struct aaclip_ctx {
   // CUDA graphs of the fused forward (aaclip_forward_fused), one per (batch, pointers, mode): the ~100 launches of a
   // chunk become one graph launch.  A key is run eagerly the first time, captured the second, replayed from then on.
   struct FusedKey {
-    const float* image; const float* anchors; float* maps; float* scores; int B; int mode;
+    const float* image; const float* anchors; float* maps; float* scores; float* minmax; int B; int mode;
     bool operator==(const FusedKey& o) const {
-      return image == o.image && anchors == o.anchors && maps == o.maps && scores == o.scores && B == o.B && mode == o.mode;
+      return image == o.image && anchors == o.anchors && maps == o.maps && scores == o.scores && minmax == o.minmax &&
+             B == o.B && mode == o.mode;
     }
   };
   struct FusedGraph { FusedKey key; cudaGraphExec_t exec; long long launches; unsigned long long last_use; };
@@ -148,7 +149,7 @@ struct aaclip_ctx {
   // host-buffer pipeline (aaclip_submit_host / aaclip_wait_host): two slots of device staging, copy-in, compute
   // and copy-out streams, so the H2D of batch k+1 and the D2H of batch k-1 overlap the compute of batch k
   struct HostSlot {
-    float *img = nullptr, *maps = nullptr, *scores = nullptr, *anchors = nullptr;
+    float *img = nullptr, *maps = nullptr, *scores = nullptr, *anchors = nullptr, *minmax = nullptr;
     uint8_t *raw = nullptr, *raw_scratch = nullptr;   // aaclip_submit_host_u8: raw images and the resample scratch
     long long raw_cap = 0, raw_scratch_cap = 0;
     cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
@@ -173,6 +174,21 @@ struct aaclip_ctx {
 };
 
 namespace {
+
+// Every entry point runs on its context's device and puts the caller's current device back on return (the thread's
+// current device belongs to the caller - PyTorch - not to this library).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(c)                                                                            \
+  DeviceGuard _guard((c)->device);                                                                 \
+  if (!_guard.ok) return host::fail(host::ERR_CUDA, "cudaSetDevice(%d) failed", (c)->device)
 
 #define TRY(expr)            \
   do {                       \
@@ -301,8 +317,8 @@ int run_block_fold(aaclip_ctx* c, const Tower& t, int i, int B, int L, float ada
 
 // seg_out[level] (fp32 [B,P,E], optional), det_out (fp32 [B,E], optional), dots (optional, [levels][B*P][2] with
 // anchors) for one chunk of B <= max_batch images.
-int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out, long long seg_off, float* det_out,
-                 const float* anchors, float* dots, cudaStream_t st) {
+int visual_chunk(aaclip_ctx* c, const float* image, int B, void* const* seg_out, int seg_is_bf16, long long seg_off,
+                 float* det_out, const float* anchors, float* dots, cudaStream_t st) {
   const aaclip_cfg& cfg = c->cfg;
   const int w = cfg.width, L = c->L, P = c->P, E = c->E, rows = B * L, prow = B * P;
   const int cg = c->cta_group;
@@ -332,7 +348,9 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
                               nullptr, st));
       const bool want_det = last && (det_out != nullptr);
       const int n_out = want_det ? 2 * E : E;
-      float* so = (seg_out && seg_out[level]) ? seg_out[level] + seg_off : nullptr;
+      // seg tokens leave as fp32 (the reference's dtype) or bf16 (half the bytes for the head to stream)
+      void* so = (seg_out && seg_out[level])
+                     ? static_cast<void*>(static_cast<uint8_t*>(seg_out[level]) + seg_off * (seg_is_bf16 ? 2 : 4)) : nullptr;
       const int act = cfg.proj_relu ? gemm::ACT_LEAKY : gemm::ACT_NONE;
       if (dots && !so && E % 128 == 0) {
         // fused path: the normalised seg tokens are never materialised - the GEMM epilogue leaves the partial sums
@@ -345,7 +363,8 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, float* const* seg_out
                            gemm::OUT_F32, nullptr, 0, cg, st));
         float* dl = dots ? dots + (size_t)level * prow * 2 : nullptr;
         if (so || dl) {
-          RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, so, nullptr, dl ? anchors : nullptr, dl, st));
+          RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, prow, E, seg_is_bf16 ? nullptr : static_cast<float*>(so),
+                                               seg_is_bf16 ? so : nullptr, dl ? anchors : nullptr, dl, st));
         }
       }
       if (want_det) { RUN(PC_DET_MEAN, k::launch_det_mean(c->s, 2 * E, E, B, P, E, c->rownorm, det_out, st)); c->launches++; }
@@ -366,7 +385,7 @@ int check_ready(const aaclip_ctx* c) {
 }  // namespace
 
 extern "C" const char* aaclip_last_error(void) { return host::last_error().c_str(); }
-extern "C" int aaclip_abi_version(void) { return 1; }
+extern "C" int aaclip_abi_version(void) { return 2; }
 
 extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device) {
   if (!out || !cfg) return host::fail(host::ERR_INVALID, "aaclip_create: null argument");
@@ -399,7 +418,8 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
                             cfg->t_vocab < 1 || cfg->text_adapt_until < 0 || cfg->text_adapt_until > cfg->t_layers))
     return host::fail(host::ERR_INVALID, "text tower config invalid");
 
-  AACLIP_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return host::fail(host::ERR_CUDA, "cudaSetDevice(%d) failed", device);
   aaclip_ctx* c = new aaclip_ctx();
   c->cfg = *cfg;
   c->device = device;
@@ -458,7 +478,7 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
 
 extern "C" void aaclip_destroy(aaclip_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   cudaDeviceSynchronize();
   for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : c->allocs) cudaFree(p);
@@ -485,7 +505,7 @@ extern "C" int aaclip_profile_enable(aaclip_ctx* c, int on) {
 // class order = ProfClass) and clears the records.  Synchronises the device.
 extern "C" int aaclip_profile_read(aaclip_ctx* c, double* ms, long long* counts, int n_classes) {
   if (!c || !ms || !counts) return host::fail(host::ERR_INVALID, "profile_read: null argument");
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  ENTER_DEVICE(c);
   AACLIP_CUDA_CHECK(cudaDeviceSynchronize());
   for (int i = 0; i < n_classes; ++i) { ms[i] = 0.0; counts[i] = 0; }
   c->prof_span_ms = 0.0;
@@ -569,7 +589,7 @@ extern "C" int aaclip_set_weight(aaclip_ctx* c, int id, int layer, const float* 
   if (dst == nullptr) return host::fail(host::ERR_STATE, "set_weight: tensor %d not allocated", id);
   if (numel != expect)
     return host::fail(host::ERR_INVALID, "set_weight: id %d layer %d expects %lld values, got %lld", id, layer, expect, numel);
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  ENTER_DEVICE(c);
   const float* dsrc = src;
   if (src_is_host) {
     if (c->stage_cap < numel) {
@@ -608,16 +628,16 @@ extern "C" int aaclip_set_weight(aaclip_ctx* c, int id, int layer, const float* 
   return host::OK;
 }
 
-extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, float* const* seg_out, float* det_out,
-                                     void* stream_) {
+extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, void* const* seg_out, int seg_is_bf16,
+                                     float* det_out, void* stream_) {
   TRY(check_ready(c));
   if (B < 0 || (B > 0 && !image)) return host::fail(host::ERR_INVALID, "visual_forward: B=%d image=%p", B, (const void*)image);
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  ENTER_DEVICE(c);
   const long long img_elems = 3LL * c->cfg.image_size * c->cfg.image_size;
   for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
     const int nb = std::min(c->cfg.max_batch, B - b0);
-    TRY(visual_chunk(c, image + b0 * img_elems, nb, seg_out, (long long)b0 * c->P * c->E,
+    TRY(visual_chunk(c, image + b0 * img_elems, nb, seg_out, seg_is_bf16 != 0, (long long)b0 * c->P * c->E,
                      det_out ? det_out + (long long)b0 * c->E : nullptr, nullptr, nullptr, st));
   }
   return host::OK;
@@ -626,22 +646,38 @@ extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, f
 namespace {
 // one chunk (<= max_batch images) of the fused forward, enqueued kernel by kernel
 int fused_chunk(aaclip_ctx* c, const float* image, int nb, const float* anchors, int mode, float* maps, float* scores,
-                cudaStream_t st) {
+                float* minmax, cudaStream_t st) {
   const int S = c->cfg.image_size;
-  TRY(visual_chunk(c, image, nb, nullptr, 0, c->det, anchors, c->dots, st));
-  if (maps) { RUN(PC_HEAD_MAPS, k::launch_head_maps(c->dots, nb, c->G, S, mode, c->cfg.n_levels, maps, st)); }
-  if (scores) { RUN(PC_OTHER, k::launch_scores(c->det, anchors, 0, nb, c->E, scores, st)); }
+  TRY(visual_chunk(c, image, nb, nullptr, 0, 0, c->det, anchors, c->dots, st));
+  // level sum -> blur -> upsample -> map rows, with the image's extrema and score from the same CTA
+  if (maps || scores) {
+    RUN(PC_HEAD_MAPS, k::launch_maps_from_dots(c->dots, c->cfg.n_levels, nb, c->G, S, mode, c->det, anchors, c->E, maps, scores,
+                                               maps ? minmax : nullptr, st));
+  }
   return host::OK;
 }
 
 // The same chunk through a CUDA graph when its key repeats (see aaclip_ctx::FusedGraph).  Not on the legacy default
-// stream (capture is not allowed there) and not while per-launch profiling is on.
+// stream (capture is not allowed there), not while per-launch profiling is on, and not when the CALLER is already
+// capturing this stream (a nested capture would invalidate theirs): then the launches simply join the caller's graph.
 int fused_chunk_graphed(aaclip_ctx* c, const float* image, int nb, const float* anchors, int mode, float* maps,
-                        float* scores, cudaStream_t st) {
-  const bool eligible = c->use_graphs && !c->prof_on && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
-  if (!eligible) return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+                        float* scores, float* minmax, cudaStream_t st) {
+  bool eligible = c->use_graphs && !c->prof_on && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  bool caller_capturing = false;
+  if (st != nullptr && st != cudaStreamLegacy) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    caller_capturing = (cs != cudaStreamCaptureStatusNone);
+  }
+  if (caller_capturing) {
+    if (c->ln_fold && c->fold_dirty)
+      return host::fail(host::ERR_STATE, "forward_fused: weights changed since the last forward; run one forward outside the "
+                                         "stream capture first (the weight re-fold is not part of the captured step)");
+    eligible = false;
+  }
+  if (!eligible) return fused_chunk(c, image, nb, anchors, mode, maps, scores, minmax, st);
   TRY(refold(c, st));   // never inside a capture: it runs only when weights changed
-  const aaclip_ctx::FusedKey key{image, anchors, maps, scores, nb, mode};
+  const aaclip_ctx::FusedKey key{image, anchors, maps, scores, minmax, nb, mode};
   ++c->graph_clock;
   for (auto& g : c->graphs)
     if (g.key == key) {
@@ -652,15 +688,15 @@ int fused_chunk_graphed(aaclip_ctx* c, const float* image, int nb, const float* 
     }
   bool seen = false;
   for (auto& k2 : c->seen_once) seen = seen || (k2 == key);
-  if (!seen) {   // first sight: run eagerly (this also performs every one-time cudaFuncSetAttribute)
+  if (!seen) {   // first sight: run eagerly
     if (c->seen_once.size() >= 64) c->seen_once.erase(c->seen_once.begin());
     c->seen_once.push_back(key);
-    return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+    return fused_chunk(c, image, nb, anchors, mode, maps, scores, minmax, st);
   }
   // second sight: capture, instantiate, launch
   const long long before = c->launches;
   AACLIP_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  const int rc = fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+  const int rc = fused_chunk(c, image, nb, anchors, mode, maps, scores, minmax, st);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(st, &graph);
   const long long n_launches = c->launches - before;
@@ -670,7 +706,7 @@ int fused_chunk_graphed(aaclip_ctx* c, const float* image, int nb, const float* 
     cudaGetLastError();
     c->use_graphs = false;   // something on the path is not capturable here: stay eager from now on
     if (rc != host::OK) return rc;
-    return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+    return fused_chunk(c, image, nb, anchors, mode, maps, scores, minmax, st);
   }
   cudaGraphExec_t exec = nullptr;
   const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
@@ -678,7 +714,7 @@ int fused_chunk_graphed(aaclip_ctx* c, const float* image, int nb, const float* 
   if (ie != cudaSuccess) {
     cudaGetLastError();
     c->use_graphs = false;
-    return fused_chunk(c, image, nb, anchors, mode, maps, scores, st);
+    return fused_chunk(c, image, nb, anchors, mode, maps, scores, minmax, st);
   }
   if (c->graphs.size() >= 16) {   // evict the least recently used
     size_t v = 0;
@@ -694,20 +730,22 @@ int fused_chunk_graphed(aaclip_ctx* c, const float* image, int nb, const float* 
 }  // namespace
 
 extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, const float* anchors, int mode,
-                                    float* maps_out, float* scores_out, void* stream_) {
+                                    float* maps_out, float* scores_out, float* minmax_out, void* stream_) {
   TRY(check_ready(c));
   if (B < 0 || (B > 0 && (!image || !anchors)))
     return host::fail(host::ERR_INVALID, "forward_fused: null argument");
   if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
     return host::fail(host::ERR_INVALID, "forward_fused: only the test modes are fused (mode=%d)", mode);
+  if (minmax_out && !maps_out) return host::fail(host::ERR_INVALID, "forward_fused: extrema are produced with the maps");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  ENTER_DEVICE(c);
   const int S = c->cfg.image_size;
   const long long img_elems = 3LL * S * S;
   for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
     const int nb = std::min(c->cfg.max_batch, B - b0);
     TRY(fused_chunk_graphed(c, image + b0 * img_elems, nb, anchors, mode,
-                            maps_out ? maps_out + (long long)b0 * S * S : nullptr, scores_out ? scores_out + b0 : nullptr, st));
+                            maps_out ? maps_out + (long long)b0 * S * S : nullptr, scores_out ? scores_out + b0 : nullptr,
+                            minmax_out ? minmax_out + 2LL * b0 : nullptr, st));
   }
   return host::OK;
 }
@@ -721,42 +759,25 @@ int ensure_host_pipeline(aaclip_ctx* c) {
   AACLIP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
   for (auto& sl : c->slots) {
     TRY(c->alloc(&sl.img, 3LL * mb * S * S)); TRY(c->alloc(&sl.maps, (long long)mb * S * S));
-    TRY(c->alloc(&sl.scores, mb)); TRY(c->alloc(&sl.anchors, 2LL * c->E));
+    TRY(c->alloc(&sl.scores, mb)); TRY(c->alloc(&sl.anchors, 2LL * c->E)); TRY(c->alloc(&sl.minmax, 2LL * mb));
     AACLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
     AACLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sl.comp_done, cudaEventDisableTiming));
     AACLIP_CUDA_CHECK(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
   }
   return host::OK;
 }
-}  // namespace
 
-namespace {
 int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host_u8, int H0, int W0, int B,
                      const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
-                     long long* ticket);
-}
-extern "C" int aaclip_submit_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors, int mode,
-                                  float* host_maps_out, float* host_scores_out, long long* ticket) {
-  if (!host_image) return host::fail(host::ERR_INVALID, "submit_host: null argument");
-  return submit_host_impl(c, host_image, nullptr, 0, 0, B, host_anchors, mode, host_maps_out, host_scores_out, ticket);
-}
-extern "C" int aaclip_submit_host_u8(aaclip_ctx* c, const uint8_t* host_u8, int B, int H0, int W0,
-                                     const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
-                                     long long* ticket) {
-  if (!host_u8 || H0 < 1 || W0 < 1) return host::fail(host::ERR_INVALID, "submit_host_u8: null image or bad size");
-  return submit_host_impl(c, nullptr, host_u8, H0, W0, B, host_anchors, mode, host_maps_out, host_scores_out, ticket);
-}
-namespace {
-int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host_u8, int H0, int W0, int B,
-                     const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
-                     long long* ticket) {
+                     float* host_minmax_out, long long* ticket) {
   TRY(check_ready(c));
   if (!host_anchors || !ticket) return host::fail(host::ERR_INVALID, "submit_host: null argument");
   if (B < 1 || B > c->cfg.max_batch)
     return host::fail(host::ERR_INVALID, "submit_host: B=%d outside [1, max_batch=%d]", B, c->cfg.max_batch);
   if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
     return host::fail(host::ERR_INVALID, "submit_host: only the test modes are fused (mode=%d)", mode);
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  if (host_minmax_out && !host_maps_out) return host::fail(host::ERR_INVALID, "submit_host: extrema are produced with the maps");
+  ENTER_DEVICE(c);
   TRY(ensure_host_pipeline(c));
   aaclip_ctx::HostSlot& sl = c->slots[c->next_ticket & 1];
   if (sl.busy)
@@ -792,7 +813,7 @@ int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host
     c->launches += (W0 != S) ? 2 : 1;
   }
   TRY(aaclip_forward_fused(c, sl.img, B, sl.anchors, mode, host_maps_out ? sl.maps : nullptr,
-                           host_scores_out ? sl.scores : nullptr, c->own_stream));
+                           host_scores_out ? sl.scores : nullptr, host_minmax_out ? sl.minmax : nullptr, c->own_stream));
   AACLIP_CUDA_CHECK(cudaEventRecord(sl.comp_done, c->own_stream));
   // copy-out
   AACLIP_CUDA_CHECK(cudaStreamWaitEvent(c->out_stream, sl.comp_done, 0));
@@ -800,6 +821,8 @@ int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host
     AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_maps_out, sl.maps, (long long)B * S * S * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
   if (host_scores_out)
     AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_scores_out, sl.scores, B * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
+  if (host_minmax_out)
+    AACLIP_CUDA_CHECK(cudaMemcpyAsync(host_minmax_out, sl.minmax, 2LL * B * sizeof(float), cudaMemcpyDeviceToHost, c->out_stream));
   AACLIP_CUDA_CHECK(cudaEventRecord(sl.out_done, c->out_stream));
   sl.busy = true;
   sl.ticket = c->next_ticket;
@@ -808,19 +831,33 @@ int submit_host_impl(aaclip_ctx* c, const float* host_image, const uint8_t* host
 }
 }  // namespace
 
+extern "C" int aaclip_submit_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors, int mode,
+                                  float* host_maps_out, float* host_scores_out, float* host_minmax_out, long long* ticket) {
+  if (!host_image) return host::fail(host::ERR_INVALID, "submit_host: null argument");
+  return submit_host_impl(c, host_image, nullptr, 0, 0, B, host_anchors, mode, host_maps_out, host_scores_out,
+                          host_minmax_out, ticket);
+}
+extern "C" int aaclip_submit_host_u8(aaclip_ctx* c, const uint8_t* host_u8, int B, int H0, int W0,
+                                     const float* host_anchors, int mode, float* host_maps_out, float* host_scores_out,
+                                     float* host_minmax_out, long long* ticket) {
+  if (!host_u8 || H0 < 1 || W0 < 1) return host::fail(host::ERR_INVALID, "submit_host_u8: null image or bad size");
+  return submit_host_impl(c, nullptr, host_u8, H0, W0, B, host_anchors, mode, host_maps_out, host_scores_out,
+                          host_minmax_out, ticket);
+}
+
 extern "C" int aaclip_wait_host(aaclip_ctx* c, long long ticket) {
   TRY(check_ready(c));
   aaclip_ctx::HostSlot& sl = c->slots[ticket & 1];
   if (ticket < 0 || sl.ticket != ticket || !sl.busy)
     return host::fail(host::ERR_STATE, "wait_host: ticket %lld is not pending", ticket);
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  ENTER_DEVICE(c);
   AACLIP_CUDA_CHECK(cudaEventSynchronize(sl.out_done));
   sl.busy = false;
   return host::OK;
 }
 
 extern "C" int aaclip_forward_fused_host(aaclip_ctx* c, const float* host_image, int B, const float* host_anchors,
-                                         int mode, float* host_maps_out, float* host_scores_out) {
+                                         int mode, float* host_maps_out, float* host_scores_out, float* host_minmax_out) {
   TRY(check_ready(c));
   if (B <= 0) return host::OK;
   for (const auto& sl : c->slots)
@@ -836,7 +873,8 @@ extern "C" int aaclip_forward_fused_host(aaclip_ctx* c, const float* host_image,
     long long t = -1;
     TRY(aaclip_submit_host(c, host_image + b0 * img_elems, nb, host_anchors, mode,
                            host_maps_out ? host_maps_out + (long long)b0 * S * S : nullptr,
-                           host_scores_out ? host_scores_out + b0 : nullptr, &t));
+                           host_scores_out ? host_scores_out + b0 : nullptr,
+                           host_minmax_out ? host_minmax_out + 2LL * b0 : nullptr, &t));
     pending[n_pending++] = t;
   }
   for (int i = 0; i < n_pending; ++i) TRY(aaclip_wait_host(c, pending[i]));
@@ -849,7 +887,7 @@ extern "C" int aaclip_text_forward(aaclip_ctx* c, const int32_t* tokens, int n, 
   if (cfg.t_layers <= 0) return host::fail(host::ERR_STATE, "text_forward: context has no text tower");
   if (n < 0 || (n > 0 && (!tokens || !out))) return host::fail(host::ERR_INVALID, "text_forward: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  AACLIP_CUDA_CHECK(cudaSetDevice(c->device));
+  ENTER_DEVICE(c);
   const int ctx = cfg.t_context, tw = cfg.t_width;
   const int chunk = std::max(1, c->cap_rows / ctx);
   for (int n0 = 0; n0 < n; n0 += chunk) {

@@ -1,17 +1,20 @@
 // Anomaly-map head: calculate_similarity_map (forward_utils.py:196-216) + the caller arithmetic of
-// test.py:83-93 (level cat + sum, image score), as two HBM-bound kernels:
+// test.py:83-93 (level cat + sum, image score).
 //
-//   patch_dots_kernel : one warp per patch token; 16-byte coalesced loads of the (bf16 or fp32) normalised
-//                       tokens of every level, warp-shuffle dot products with both text anchors.
-//   head_maps_kernel  : per (image, band of output rows): level-summed patch map in smem, separable gaussian
-//                       blur with reflect padding on the G x G grid, then the align_corners=True bilinear
-//                       upsample as 4 taps per output pixel, float4 coalesced stores of the fp32 map.
-//                       Train mode (test=False): no blur, both channels, softmax over channels, per level.
+//   test modes, shared anchors, E = 768 (what test.py runs): head_stream_kernel (head_stream.cu), one launch.
+//   fused engine path (dots already left by the seg_proj GEMM epilogue): maps_from_dots_kernel below - one CTA per
+//                       image: level sum, blur, upsample, map rows, extrema, score (head_epilogue.cuh).
+//   general form (train mode = softmax over the two channels per level, per-image anchors, other E):
+//     patch_dots_kernel : one warp per patch token; 16-byte coalesced loads of the (bf16 or fp32) normalised
+//                         tokens of every level, warp-shuffle dot products with both text anchors.
+//     head_maps_kernel  : per (image, band of output rows): patch map in smem, optional separable gaussian blur
+//                         with reflect padding, align_corners=True bilinear upsample as 4 taps per output pixel.
 //
 // Test mode, summed over levels (test.py:93):   m[h][w] = sum_l (100*(d1-d0) + 1)/2 = 50*sum_l(d1-d0) + n_levels/2
 #include <stdarg.h>
 #include <algorithm>
 #include "common.cuh"
+#include "head_epilogue.cuh"
 #include "internal.h"
 #include "ptx.cuh"
 #include "../../include/aaclip_b200.h"
@@ -62,50 +65,6 @@ patch_dots_kernel(SegPtrs seg, int n_levels, const float* __restrict__ anchors, 
     if (lane == 0) {
       float2 o = make_float2(d0, d1);
       *reinterpret_cast<float2*>(dots + ((size_t)l * rows + row) * 2) = o;
-    }
-  }
-}
-
-// Streaming form for the A7 contract (bf16 tokens, E = 768, shared anchors): the lane's 24 anchor pairs live in
-// registers for the whole kernel, each warp walks rows with a grid stride and issues the 16-byte loads of ALL
-// levels of a row (up to 12 per lane) before it touches any of them, so enough bytes are in flight to run at HBM
-// speed (the general form above had 3).
-template <int NL>
-__global__ void __launch_bounds__(256)
-patch_dots_stream_kernel(SegPtrs seg, const float* __restrict__ anchors, int rows, float* __restrict__ dots) {
-  ptx::grid_dep_sync();
-  constexpr int E = 768, CH = E / 256;   // 3 chunks of 8 elements per lane
-  const int lane = threadIdx.x & 31;
-  float2 t[CH][8];                        // anchors of this lane's columns: (T[c][0], T[c][1])
-#pragma unroll
-  for (int i = 0; i < CH; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[i][j] = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
-  const int warps = gridDim.x * 8;
-  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += warps) {
-    uint4 raw[NL][CH];
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(seg.p[l]) + (size_t)row * E + lane * 8;
-#pragma unroll
-      for (int i = 0; i < CH; ++i) raw[l][i] = __ldcs(reinterpret_cast<const uint4*>(f + i * 256));   // streamed once
-    }
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[l][i]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 v = __bfloat1622float2(h[j]);
-          d0 += v.x * t[i][2 * j].x + v.y * t[i][2 * j + 1].x;
-          d1 += v.x * t[i][2 * j].y + v.y * t[i][2 * j + 1].y;
-        }
-      }
-      d0 = ptx::warp_sum(d0);
-      d1 = ptx::warp_sum(d1);
-      if (lane == 0) *reinterpret_cast<float2*>(dots + ((size_t)l * rows + row) * 2) = make_float2(d0, d1);
     }
   }
 }
@@ -245,153 +204,29 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
   }
 }
 
-// ---- the A7 contract as ONE kernel (test modes, bf16 tokens, E = 768, shared anchors) -----------------------------
-// A thread-block cluster of 8 CTAs per image.  Phase 1: CTA r reads patches [r*P/8, (r+1)*P/8) of all levels
-// (every 16-byte load of a row issued before the first use; the lane's 24 anchor pairs stay in registers) and
-// leaves the level-summed scalars m in ITS shared memory.  After a cluster barrier every CTA gathers the whole
-// G x G map through distributed shared memory, blurs it, and writes 1/8 of the image's output rows with float4
-// stores; CTA 0 also produces the image score.  Bytes moved = the algorithmic 3.99 MB/image, once.
-constexpr int FUSED_CLUSTER = 8;
-constexpr int FUSED_THREADS = 128;
-template <int NL>
-__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, 4)
-head_fused_kernel(SegPtrs seg, const float* __restrict__ anchors, const float* __restrict__ det, int P, int G, int S,
-                  int mode, float* __restrict__ maps, float* __restrict__ scores) {
+// ---- fused engine path, test modes: dots [n_levels][B*P][2] (left by the seg_proj GEMM epilogue + dots_finish) ->
+// level-summed patch map -> blur -> upsample -> map rows, extrema, image score.  One CTA (8 warps) per image.
+__global__ void __launch_bounds__(headepi::THREADS)
+maps_from_dots_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int S, int ksize, float sigma,
+                      const float* __restrict__ det, const float* __restrict__ anchors, int E, float* __restrict__ maps,
+                      float* __restrict__ scores, float* __restrict__ minmax) {
+  extern __shared__ __align__(16) float epi_sm[];
+  const int P = G * G, b = blockIdx.x, tid = threadIdx.x;
+  const headepi::Smem e = headepi::carve(epi_sm, P, G, S);
+  headepi::setup(e, tid, headepi::THREADS, G, S, ksize, sigma);
   ptx::grid_dep_sync();
-  constexpr int E = 768, CH = E / 256;
-  extern __shared__ float sm[];
-  float* m_part = sm;                 // [chunk]   this CTA's patches
-  float* m = sm + 96;                 // [P]       whole map (gathered), chunk <= 96 keeps the offset fixed
-  float* t = m + P;                   // [P]       after the row blur
-  float* mb = t + P;                  // [P]       blurred map
-  __shared__ float wk[16];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t rank = ptx::cluster_ctarank();
-  const int b = blockIdx.x / FUSED_CLUSTER;
-  const int chunk = (P + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
-  const int ksize = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 7 : 9;
-  const float sigma = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 1.0f : 1.5f;
-  if (tid == 0) {
-    float sum = 0.f;
-    for (int i = 0; i < ksize; ++i) {
-      const float x = float(i - ksize / 2);
-      wk[i] = expf(-(x * x) / (2.0f * sigma * sigma));
-      sum += wk[i];
-    }
-    for (int i = 0; i < ksize; ++i) wk[i] /= sum;
-  }
-  // ---- phase 1: anchor dots of this CTA's patches
-  // the test-mode map needs only (s1 - s0) per level: ((100 d1) + 1 - (100 d0)) / 2 = 50 <f, T1 - T0> + 0.5, so a lane
-  // keeps the 24 DIFFERENCES of its anchor pairs (half the registers and FMAs of two separate dot products)
-  float td[CH][8];
-#pragma unroll
-  for (int i = 0; i < CH; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 t2 = __ldg(reinterpret_cast<const float2*>(anchors + (size_t)(i * 256 + lane * 8 + j) * 2));
-      td[i][j] = t2.y - t2.x;
-    }
-  const int p_end = min(P, int(rank + 1) * chunk);
-  // PP patches per warp and iteration: all PP * NL * CH 16-byte loads of a lane are in flight before the first use
-  // (memory-level parallelism is what bounds this phase: 6 KB per warp and patch)
-  constexpr int PP = 2, WARPS = FUSED_THREADS / 32;
-  for (int p0 = int(rank) * chunk + warp; p0 < p_end; p0 += WARPS * PP) {
-    uint4 raw[PP][NL][CH];
-#pragma unroll
-    for (int u = 0; u < PP; ++u) {
-      const int p = min(p0 + u * WARPS, p_end - 1);   // a clamped duplicate is computed and dropped
-      const size_t row = (size_t)b * P + p;
-#pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(seg.p[l]) + row * E + lane * 8;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) raw[u][l][i] = __ldcs(reinterpret_cast<const uint4*>(f + i * 256));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < PP; ++u) {
-      float acc = 0.f;
-#pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u][l][i]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 v = __bfloat1622float2(h[j]);
-            d = fmaf(v.x, td[i][2 * j], fmaf(v.y, td[i][2 * j + 1], d));
-          }
-        }
-        d = ptx::warp_sum(d);
-        acc += fmaf(50.0f, d, 0.5f);   // (s1 + 1 - s0) / 2 of this level (test.py:85)
-      }
-      const int p = p0 + u * WARPS;
-      if (lane == 0 && p < p_end) m_part[p - int(rank) * chunk] = acc;
-    }
-  }
-  // image score (test.py:83-84) by one warp of the cluster's first CTA
-  if (rank == 0 && warp == 0 && scores != nullptr) {
+  const size_t rows = (size_t)B * P;
+  for (int i = tid; i < P; i += headepi::THREADS) {
     float acc = 0.f;
-    for (int c = lane; c < E; c += 32) acc += det[(size_t)b * E + c] * __ldg(anchors + c * 2 + 1);
-    acc = ptx::warp_sum(acc);
-    if (lane == 0) scores[b] = (acc + 1.0f) * 0.5f;
+    for (int l = 0; l < n_levels; ++l) {
+      const float2 d = *reinterpret_cast<const float2*>(dots + ((size_t)l * rows + (size_t)b * P + i) * 2);
+      acc += (100.0f * d.y + 1.0f - 100.0f * d.x) * 0.5f;   // per level exactly as the reference (test.py:85)
+    }
+    e.m[i] = acc;
   }
-  ptx::cluster_sync();
-  // ---- gather the whole map through distributed shared memory
-  for (int i = tid; i < P; i += FUSED_THREADS) {
-    const uint32_t src_rank = uint32_t(i / chunk);
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(m_part + (i - int(src_rank) * chunk))), "r"(src_rank));
-    float v;
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-    m[i] = v;
-  }
-  ptx::cluster_sync();   // nobody's m_part may disappear (CTA exit) before every peer has read it
-  // ---- blur along x, then along y (reflect padding: forward_utils.py:208-210)
-  const int half = ksize / 2;
-  for (int i = tid; i < P; i += FUSED_THREADS) {
-    const int gy = i / G, gx = i - gy * G;
-    float acc = 0.f;
-    for (int k = 0; k < ksize; ++k) acc += wk[k] * m[gy * G + reflect_idx(gx + k - half, G)];
-    t[i] = acc;
-  }
+  if (tid < 32 && scores != nullptr) headepi::image_score(det, anchors, E, b, tid, scores);
   __syncthreads();
-  for (int i = tid; i < P; i += FUSED_THREADS) {
-    const int gy = i / G, gx = i - gy * G;
-    float acc = 0.f;
-    for (int k = 0; k < ksize; ++k) acc += wk[k] * t[reflect_idx(gy + k - half, G) * G + gx];
-    mb[i] = acc;
-  }
-  __syncthreads();
-  // ---- bilinear, align_corners=True (forward_utils.py:211-213): this CTA's share of the output rows
-  const float scale = (S > 1) ? float(G - 1) / float(S - 1) : 0.f;
-  const int rows_per = (S + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
-  const int y0 = int(rank) * rows_per, ny = max(0, min(rows_per, S - y0));
-  const int xq = (S + 3) / 4;
-  for (int i = tid; i < ny * xq; i += FUSED_THREADS) {
-    const int yy = i / xq, x4 = (i - yy * xq) * 4;
-    const int y = y0 + yy;
-    const float sy = scale * float(y);
-    const int ry0 = min(int(sy), G - 1);
-    const int ry1 = ry0 + ((ry0 < G - 1) ? 1 : 0);
-    const float ly1 = sy - float(ry0), ly0 = 1.0f - ly1;
-    float o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int x = min(x4 + e, S - 1);
-      const float sx = scale * float(x);
-      const int rx0 = min(int(sx), G - 1);
-      const int rx1 = rx0 + ((rx0 < G - 1) ? 1 : 0);
-      const float lx1 = sx - float(rx0), lx0 = 1.0f - lx1;
-      const float top = lx0 * mb[ry0 * G + rx0] + lx1 * mb[ry0 * G + rx1];
-      const float bot = lx0 * mb[ry1 * G + rx0] + lx1 * mb[ry1 * G + rx1];
-      o[e] = ly0 * top + ly1 * bot;
-    }
-    float* dst = maps + ((size_t)b * S + y) * S + x4;
-    if (x4 + 3 < S && (S & 3) == 0) __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
-    else for (int e = 0; e < 4 && x4 + e < S; ++e) dst[e] = o[e];
-  }
+  if (maps != nullptr) headepi::image(e, tid, b, G, S, ksize, maps, minmax, [] { __syncthreads(); });
 }
 
 // scores[b] = (<det[b], anchors[:,1]> + 1) / 2      (test.py:83-84)
@@ -455,18 +290,6 @@ int k::launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, 
   }
   const int rows = B * P;
   const int blocks = (rows + 7) / 8;
-  if (seg_is_bf16 && !anchors_batched && E == 768 && (n_levels == 4 || n_levels == 1)) {
-    // streaming form: each warp walks rows with a grid stride
-    int dev = 0;
-    AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
-    const int sms = host::sm_count(dev) > 0 ? host::sm_count(dev) : 148;
-    const int grid = std::min(blocks, sms * 2);   // 105 registers: two resident blocks per SM
-    if (n_levels == 4)
-      AACLIP_CUDA_CHECK(host::launch(patch_dots_stream_kernel<4>, dim3(grid), dim3(256), 0, stream, sp, anchors, rows, dots));
-    else
-      AACLIP_CUDA_CHECK(host::launch(patch_dots_stream_kernel<1>, dim3(grid), dim3(256), 0, stream, sp, anchors, rows, dots));
-    return host::OK;
-  }
   if (seg_is_bf16)
     AACLIP_CUDA_CHECK(host::launch(patch_dots_kernel<true>, dim3(blocks), dim3(256), 0, stream, sp, n_levels, anchors,
                                    anchors_batched, rows, P, E, dots));
@@ -483,13 +306,32 @@ int k::launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_
   if (G <= pad) return host::fail(host::ERR_INVALID, "head: grid %d too small for reflect padding %d", G, pad);
   const size_t smem = (size_t)6 * G * G * sizeof(float);
   if (smem > 200 * 1024) return host::fail(host::ERR_INVALID, "head: img_size %d / grid %d needs %zu B smem", S, G, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
+  // per call: the attribute belongs to the current device's context (one process may hold several contexts)
+  if (smem > 48 * 1024)
     AACLIP_CUDA_CHECK(cudaFuncSetAttribute(head_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   dim3 grid((S + BAND - 1) / BAND, B, mode == AACLIP_HEAD_TRAIN_SOFTMAX ? n_levels : 1);
   AACLIP_CUDA_CHECK(host::launch(head_maps_kernel, grid, dim3(HEAD_THREADS), smem, stream, dots, n_levels, B, G, S, mode, maps));
+  return host::OK;
+}
+
+// Test modes from precomputed dots: level sum -> blur -> upsample -> maps (+ extrema, + image scores), one launch.
+int k::launch_maps_from_dots(const float* dots, int n_levels, int B, int G, int S, int mode, const float* det,
+                             const float* anchors, int E, float* maps, float* scores, float* minmax,
+                             cudaStream_t stream) {
+  if (B <= 0) return host::OK;
+  if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
+    return host::fail(host::ERR_INVALID, "head: maps_from_dots is test-mode only (mode %d)", mode);
+  const int pad = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 3 : 4;
+  if (G <= pad) return host::fail(host::ERR_INVALID, "head: grid %d too small for reflect padding %d", G, pad);
+  if (scores != nullptr && (det == nullptr || anchors == nullptr))
+    return host::fail(host::ERR_INVALID, "head: scores requested without det / anchors");
+  const size_t smem = headepi::smem_floats(G * G, G, S) * sizeof(float);
+  if (smem > 200 * 1024) return host::fail(host::ERR_INVALID, "head: img_size %d / grid %d needs %zu B smem", S, G, smem);
+  if (smem > 48 * 1024)
+    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(maps_from_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AACLIP_CUDA_CHECK(host::launch(maps_from_dots_kernel, dim3(B), dim3(headepi::THREADS), smem, stream, dots, n_levels, B, G, S,
+                                 pad * 2 + 1, mode == AACLIP_HEAD_TEST_INDUSTRIAL ? 1.0f : 1.5f, det, anchors, E, maps, scores,
+                                 minmax));
   return host::OK;
 }
 
@@ -500,55 +342,49 @@ int k::launch_scores(const float* det, const float* anchors, int anchors_batched
   return host::OK;
 }
 
-// Scratch for the standalone head entry (dots are tiny: n_levels * B * P * 2 floats).
-namespace {
-struct DotScratch { float* p = nullptr; size_t cap = 0; int dev = -1; };
-DotScratch g_scratch;
+// Device scratch the head needs from its caller (the library allocates nothing per call, so the entry is capturable
+// and safe on any stream): the streaming kernel's per-patch scalars + counters, or the general form's dots.
+extern "C" long long aaclip_anomaly_head_workspace_bytes(int n_levels, int B, int P) {
+  if (n_levels < 1 || B < 0 || P < 0) return 0;
+  const long long dots = (long long)n_levels * B * P * 2 * (long long)sizeof(float);
+  return std::max(dots, k::head_stream_workspace_bytes(B, P)) + 256;
 }
 
 extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors,
                                    int anchors_batched, const float* det, int B, int P, int E, int img_size, int mode,
-                                   float* maps_out, float* scores_out, void* stream_) {
+                                   float* maps_out, float* scores_out, float* minmax_out, void* workspace,
+                                   long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (B <= 0) return host::OK;  // empty batch: nothing to do
+  if (!seg || !anchors || n_levels < 1 || n_levels > MAX_LEVELS)
+    return host::fail(host::ERR_INVALID, "head: seg / anchors missing or n_levels=%d", n_levels);
   int G = 0;
   while ((G + 1) * (G + 1) <= P) ++G;  // H = int(sqrt(L)), forward_utils.py:201
   if (G * G != P) return host::fail(host::ERR_INVALID, "head: P=%d is not a square grid", P);
+  if (scores_out != nullptr && det == nullptr) return host::fail(host::ERR_INVALID, "head: scores requested without det");
   const bool test_mode = (mode == AACLIP_HEAD_TEST_INDUSTRIAL || mode == AACLIP_HEAD_TEST_MEDICAL);
-  const int pad = (mode == AACLIP_HEAD_TEST_INDUSTRIAL) ? 3 : 4;
-  if (maps_out != nullptr && test_mode && seg_is_bf16 && !anchors_batched && E == 768 && (n_levels == 4 || n_levels == 1) &&
-      (P + FUSED_CLUSTER - 1) / FUSED_CLUSTER <= 96 && G > pad && (scores_out == nullptr || det != nullptr)) {
-    // the whole head in one launch: cluster of 8 CTAs per image (head_fused_kernel)
-    SegPtrs sp;
-    for (int l = 0; l < n_levels; ++l) {
-      if (seg[l] == nullptr) return host::fail(host::ERR_INVALID, "head: seg[%d] is NULL", l);
-      sp.p[l] = seg[l];
-    }
-    const size_t smem = (96 + 3 * (size_t)P) * sizeof(float);
-    if (n_levels == 4)
-      AACLIP_CUDA_CHECK(host::launch(head_fused_kernel<4>, dim3(B * FUSED_CLUSTER), dim3(FUSED_THREADS), smem, stream, sp, anchors,
-                                     det, P, G, img_size, mode, maps_out, scores_out));
-    else
-      AACLIP_CUDA_CHECK(host::launch(head_fused_kernel<1>, dim3(B * FUSED_CLUSTER), dim3(FUSED_THREADS), smem, stream, sp, anchors,
-                                     det, P, G, img_size, mode, maps_out, scores_out));
-    return host::OK;
-  }
+  if (minmax_out != nullptr && (!test_mode || maps_out == nullptr))
+    return host::fail(host::ERR_INVALID, "head: extrema are produced with the test-mode maps only");
   if (maps_out != nullptr) {
-    int dev = 0;
-    AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
-    const size_t need = (size_t)n_levels * B * P * 2 * sizeof(float);
-    if (g_scratch.dev != dev || g_scratch.cap < need) {
-      if (g_scratch.p) { cudaStreamSynchronize(stream); cudaFree(g_scratch.p); g_scratch.p = nullptr; }
-      AACLIP_CUDA_CHECK(cudaMalloc(&g_scratch.p, need));
-      g_scratch.cap = need; g_scratch.dev = dev;
-    }
-    int rc = k::launch_patch_dots(seg, n_levels, seg_is_bf16, anchors, anchors_batched, B, P, E, g_scratch.p, stream);
+    if (workspace == nullptr || workspace_bytes < aaclip_anomaly_head_workspace_bytes(n_levels, B, P) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
+      return host::fail(host::ERR_INVALID, "head: workspace of %lld bytes (16-byte aligned) required, got %lld",
+                        aaclip_anomaly_head_workspace_bytes(n_levels, B, P), workspace_bytes);
+    if (k::head_stream_supported(n_levels, seg_is_bf16, anchors_batched, E, P, G, img_size, mode, seg))
+      // the whole head in one launch (head_stream.cu): tokens streamed once, maps + extrema + scores written once
+      return k::launch_head_stream(seg, n_levels, seg_is_bf16, anchors, det, B, P, G, img_size, mode, maps_out, scores_out,
+                                   minmax_out, workspace, stream);
+    float* dots = static_cast<float*>(workspace);
+    int rc = k::launch_patch_dots(seg, n_levels, seg_is_bf16, anchors, anchors_batched, B, P, E, dots, stream);
     if (rc) return rc;
-    rc = k::launch_head_maps(g_scratch.p, B, G, img_size, mode, n_levels, maps_out, stream);
+    if (test_mode && !anchors_batched)
+      return k::launch_maps_from_dots(dots, n_levels, B, G, img_size, mode, det, anchors, E, maps_out, scores_out, minmax_out,
+                                      stream);
+    if (minmax_out != nullptr) return host::fail(host::ERR_INVALID, "head: extrema need shared anchors");
+    rc = k::launch_head_maps(dots, B, G, img_size, mode, n_levels, maps_out, stream);
     if (rc) return rc;
   }
   if (scores_out != nullptr) {
-    if (det == nullptr) return host::fail(host::ERR_INVALID, "head: scores requested without det");
     int rc = k::launch_scores(det, anchors, anchors_batched, B, E, scores_out, stream);
     if (rc) return rc;
   }

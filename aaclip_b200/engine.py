@@ -153,21 +153,32 @@ class Engine:
         if not image.is_cuda or image.dtype != torch.float32 or not image.is_contiguous():
             raise ValueError("image must be a contiguous float32 CUDA tensor")
 
-    def visual_forward(self, image: torch.Tensor, want_seg: bool = True, want_det: bool = True):
-        """AdaptedCLIP.forward: returns (list of fp32 [B,P,E], fp32 [B,E])."""
+    def _stream(self) -> int:
+        return cur_stream(self.device)
+
+    def visual_forward(self, image: torch.Tensor, want_seg: bool = True, want_det: bool = True,
+                       seg_dtype: torch.dtype = torch.float32):
+        """AdaptedCLIP.forward: returns (list of [B,P,E] L2-normalised patch tokens, fp32 [B,E]).  `seg_dtype` is
+        torch.float32 (what the reference returns) or torch.bfloat16 (half the bytes for the anomaly-map head)."""
         self._check_image(image)
+        if seg_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("seg_dtype must be torch.float32 or torch.bfloat16")
         B = image.shape[0]
         cfg = self.cfg
-        seg = [torch.empty(B, cfg.patches, cfg.embed_dim, device=image.device, dtype=torch.float32)
+        seg = [torch.empty(B, cfg.patches, cfg.embed_dim, device=image.device, dtype=seg_dtype)
                for _ in cfg.levels] if want_seg else []
         det = torch.empty(B, cfg.embed_dim, device=image.device, dtype=torch.float32) if want_det else None
         arr = (C.c_void_p * len(cfg.levels))(*[t.data_ptr() for t in seg]) if want_seg else None
-        check(self.lib.aaclip_visual_forward(self._ctx, ptr(image), B, arr, ptr(det), cur_stream()))
+        check(self.lib.aaclip_visual_forward(self._ctx, ptr(image), B, arr, int(seg_dtype == torch.bfloat16), ptr(det),
+                                             self._stream()))
         return seg, det
 
     def forward_fused(self, image: torch.Tensor, anchors: torch.Tensor, domain: str = "Industrial",
-                      want_maps: bool = True, want_scores: bool = True, out=None):
+                      want_maps: bool = True, want_scores: bool = True, out=None, extrema: Optional[torch.Tensor] = None):
         """image -> (level-summed anomaly maps fp32 [B,S,S], image scores fp32 [B]) without seg tokens.
+
+        `extrema`: optional float32 CUDA tensor [B,2] that receives every image's (min, max) over its map, written by
+        the head's own epilogue (the pixel-side input of metrics_eval, forward_utils.py:241-252).
 
         `out = (maps, scores)` reuses caller-owned output tensors.  On a non-default stream a call whose pointers
         (image, anchors, outputs) and batch repeat is replayed as ONE CUDA graph launch (captured at its second
@@ -186,57 +197,65 @@ class Engine:
         else:
             maps = torch.empty(B, S, S, device=image.device, dtype=torch.float32) if want_maps else None
             scores = torch.empty(B, device=image.device, dtype=torch.float32) if want_scores else None
+        if extrema is not None and (tuple(extrema.shape) != (B, 2) or extrema.dtype != torch.float32 or not extrema.is_cuda
+                                    or not extrema.is_contiguous() or maps is None):
+            raise ValueError(f"extrema must be a contiguous float32 CUDA tensor [{B},2] (and maps must be requested)")
         check(self.lib.aaclip_forward_fused(self._ctx, ptr(image), B, ptr(anchors.contiguous()), DOMAIN_MODE[domain],
-                                            ptr(maps), ptr(scores), cur_stream()))
+                                            ptr(maps), ptr(scores), ptr(extrema), self._stream()))
         return maps, scores
 
+    @staticmethod
+    def _host_f32(tensors, what: str) -> None:
+        for t in tensors:
+            if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise ValueError(f"{what} takes contiguous float32 CPU tensors")
+
     def forward_fused_host(self, image: torch.Tensor, anchors: torch.Tensor, maps_out: torch.Tensor,
-                           scores_out: torch.Tensor, domain: str = "Industrial") -> None:
-        """Host-buffer entry: `image`, `anchors`, `maps_out`, `scores_out` are CPU tensors (pinned for speed);
-        H2D, compute and D2H all happen inside the call, which returns after the results have landed."""
-        for t in (image, anchors, maps_out, scores_out):
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("forward_fused_host takes contiguous float32 CPU tensors")
+                           scores_out: torch.Tensor, domain: str = "Industrial",
+                           extrema_out: Optional[torch.Tensor] = None) -> None:
+        """Host-buffer entry: `image`, `anchors`, `maps_out`, `scores_out` (and `extrema_out` [B,2]) are CPU tensors
+        (pinned for speed); H2D, compute and D2H all happen inside the call, which returns after the results landed."""
+        self._host_f32((image, anchors, maps_out, scores_out, extrema_out), "forward_fused_host")
         check(self.lib.aaclip_forward_fused_host(self._ctx, image.data_ptr(), image.shape[0], anchors.data_ptr(),
-                                                 DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr()))
+                                                 DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr(),
+                                                 ptr(extrema_out)))
 
     def submit_host(self, image: torch.Tensor, anchors: torch.Tensor, maps_out: torch.Tensor,
-                    scores_out: torch.Tensor, domain: str = "Industrial") -> int:
+                    scores_out: torch.Tensor, domain: str = "Industrial",
+                    extrema_out: Optional[torch.Tensor] = None) -> int:
         """Asynchronous host-buffer entry: enqueues H2D -> forward -> D2H for one batch (<= max_batch images) and
         returns a ticket; at most two tickets may be pending.  The CPU tensors must stay alive until wait_host."""
-        for t in (image, anchors, maps_out, scores_out):
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("submit_host takes contiguous float32 CPU tensors")
+        self._host_f32((image, anchors, maps_out, scores_out, extrema_out), "submit_host")
         ticket = C.c_longlong(-1)
         check(self.lib.aaclip_submit_host(self._ctx, image.data_ptr(), image.shape[0], anchors.data_ptr(),
                                           DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr(),
-                                          C.byref(ticket)))
+                                          ptr(extrema_out), C.byref(ticket)))
         return int(ticket.value)
 
     def submit_host_u8(self, image_u8: torch.Tensor, anchors: torch.Tensor, maps_out: torch.Tensor,
-                       scores_out: torch.Tensor, domain: str = "Industrial") -> int:
+                       scores_out: torch.Tensor, domain: str = "Industrial",
+                       extrema_out: Optional[torch.Tensor] = None) -> int:
         """submit_host for RAW images: `image_u8` is a CPU uint8 tensor [B,H0,W0,3] (RGB, as PIL decodes it); the
         reference's transform_x (dataset/__init__.py:127-136) runs on the device, bit-exact with PIL + torchvision."""
         if image_u8.is_cuda or image_u8.dtype != torch.uint8 or not image_u8.is_contiguous() or image_u8.dim() != 4 \
                 or image_u8.shape[3] != 3:
             raise ValueError("submit_host_u8 takes a contiguous uint8 CPU tensor [B,H0,W0,3]")
-        for t in (anchors, maps_out, scores_out):
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
-                raise ValueError("submit_host_u8 takes contiguous float32 CPU tensors for anchors and outputs")
+        self._host_f32((anchors, maps_out, scores_out, extrema_out), "submit_host_u8 (anchors and outputs)")
         ticket = C.c_longlong(-1)
         B, H0, W0, _ = image_u8.shape
         check(self.lib.aaclip_submit_host_u8(self._ctx, image_u8.data_ptr(), B, H0, W0, anchors.data_ptr(),
                                              DOMAIN_MODE[domain], maps_out.data_ptr(), scores_out.data_ptr(),
-                                             C.byref(ticket)))
+                                             ptr(extrema_out), C.byref(ticket)))
         return int(ticket.value)
 
     def wait_host(self, ticket: int) -> None:
         check(self.lib.aaclip_wait_host(self._ctx, ticket))
 
-    def predict_stream(self, batches, anchors: torch.Tensor, domain: str = "Industrial"):
+    def predict_stream(self, batches, anchors: torch.Tensor, domain: str = "Industrial", with_extrema: bool = False):
         """The loop of test.py:get_predictions (test.py:53-99) over an iterable of CPU image batches, pipelined:
         while batch k computes, batch k+1 uploads and batch k-1 downloads.  Yields (maps [B,S,S], scores [B]) as
-        pinned CPU tensors, in order.  A batch is either float32 [B,3,S,S] (already transformed, as the reference's
+        pinned CPU tensors, in order; with `with_extrema` a third tensor [B,2] = per-image (min, max) of the maps
+        (from the head's epilogue: metrics_eval's normalisation then needs no pass over the pixels).  A batch is either float32 [B,3,S,S] (already transformed, as the reference's
         DataLoader delivers it) or uint8 [B,H0,W0,3] raw RGB, in which case the loader's transform_x
         (dataset/__init__.py:127-136) also runs on the device.  Batches larger than `max_batch` are split into chunks."""
         S = self.cfg.image_size
@@ -262,14 +281,16 @@ class Engine:
             n = img.shape[0]
             maps = torch.empty(n, S, S).pin_memory()
             scores = torch.empty(n).pin_memory()
-            rec = {"left": 0, "out": (maps, scores), "keep": img}
+            ext = torch.empty(n, 2).pin_memory() if with_extrema else None
+            rec = {"left": 0, "out": (maps, scores, ext) if with_extrema else (maps, scores), "keep": img}
             ready.append(rec)
             submit = self.submit_host_u8 if raw else self.submit_host
             for b0 in range(0, n, self.max_batch):   # a batch larger than max_batch rides the two slots in chunks
                 b1 = min(n, b0 + self.max_batch)
                 if len(inflight) == 2:
                     drain_one()
-                inflight.append((submit(img[b0:b1], anchors, maps[b0:b1], scores[b0:b1], domain), rec))
+                inflight.append((submit(img[b0:b1], anchors, maps[b0:b1], scores[b0:b1], domain,
+                                        ext[b0:b1] if with_extrema else None), rec))
                 rec["left"] += 1
             while ready and ready[0]["left"] == 0 and all(r is not ready[0] for _, r in inflight):
                 yield ready.pop(0)["out"]
@@ -288,5 +309,5 @@ class Engine:
             raise ValueError(f"tokens must be [n,{self.cfg.t_context}]")
         tk = tokens.to(device=f"cuda:{self.device}", dtype=torch.int32).contiguous()
         out = torch.empty(tk.shape[0], self.cfg.t_width, device=tk.device, dtype=torch.float32)
-        check(self.lib.aaclip_text_forward(self._ctx, ptr(tk), tk.shape[0], ptr(out), cur_stream()))
+        check(self.lib.aaclip_text_forward(self._ctx, ptr(tk), tk.shape[0], ptr(out), self._stream()))
         return out

@@ -44,12 +44,15 @@ def calculate_similarity_map(patch_features: torch.Tensor, epoch_text_feature: t
 
 @torch.no_grad()
 def similarity_maps_summed(patch_features: Sequence[torch.Tensor], epoch_text_feature: torch.Tensor, img_size: int,
-                           domain: str = "Industrial", det_feature: torch.Tensor = None):
+                           domain: str = "Industrial", det_feature: torch.Tensor = None, with_extrema: bool = False):
     """test.py:83-93 in one call: torch.cat([calculate_similarity_map(f, ..., test=True) ...], 1).sum(1) and
-    (optionally) the image score ((det @ T)[:, 1] + 1) / 2."""
-    feats = [f.contiguous() for f in patch_features]
+    (optionally) the image score ((det @ T)[:, 1] + 1) / 2 - one launch of the streaming head kernel that reads every
+    level's tokens (fp32 as the reference's model returns them, or bf16) once.  `with_extrema` adds the per-image
+    (min, max) [B,2] of the maps (metrics_eval's normalisation input, forward_utils.py:241-252)."""
+    feats = [(f if f.dtype in (torch.float32, torch.bfloat16) else f.float()).contiguous() for f in patch_features]
     return ops.anomaly_head(feats, epoch_text_feature.float().contiguous(), int(img_size), _mode(True, domain),
-                            det=None if det_feature is None else det_feature.float().contiguous())
+                            det=None if det_feature is None else det_feature.float().contiguous(),
+                            want_extrema=with_extrema)
 
 
 @torch.no_grad()
@@ -60,7 +63,7 @@ def class_text_embedding(model, tokens_normal: torch.Tensor, tokens_abnormal: to
     out = torch.empty(embs[0].shape[1], 2, device=embs[0].device, dtype=torch.float32)
     lib = load()
     for col, e in enumerate(embs):
-        check(lib.aaclip_text_anchor(ptr(e), e.shape[0], e.shape[1], ptr(out), col, cur_stream()))
+        check(lib.aaclip_text_anchor(ptr(e), e.shape[0], e.shape[1], ptr(out), col, cur_stream(e.device)))
     return out
 
 

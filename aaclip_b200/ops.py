@@ -52,7 +52,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     _need(out, torch.bfloat16 if out_mode == OUT_BF16 else torch.float32, "out")
     lib = _lib.load()
     check(lib.aaclip_gemm_bf16(ptr(a), K, ptr(w), K, M, N, K, ptr(bias), ptr(out), out.shape[-1], act, out_mode,
-                               ptr(pos), patches, cta_group, cur_stream()))
+                               ptr(pos), patches, cta_group, cur_stream(a.device)))
     return out
 
 
@@ -63,7 +63,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     ob = torch.empty(rows, width, device=x.device, dtype=torch.bfloat16) if out_bf16 else None
     of = torch.empty_like(x) if out_f32 else None
     check(_lib.load().aaclip_layernorm(ptr(x), ptr(gamma), ptr(beta), eps, rows, width, ptr(ob), ptr(of),
-                                       cur_stream()))
+                                       cur_stream(x.device)))
     return ob, of
 
 
@@ -73,7 +73,7 @@ def attention(qkv: torch.Tensor, B: int, L: int, heads: int, causal: bool = Fals
     if tuple(qkv.shape) != (B * L, 3 * heads * 64):
         raise ValueError(f"qkv shape {tuple(qkv.shape)} != ({B * L}, {3 * heads * 64})")
     out = torch.empty(B * L, heads * 64, device=qkv.device, dtype=torch.bfloat16)
-    check(_lib.load().aaclip_attention(ptr(qkv), ptr(out), B, L, heads, int(causal), cur_stream()))
+    check(_lib.load().aaclip_attention(ptr(qkv), ptr(out), B, L, heads, int(causal), cur_stream(qkv.device)))
     return out
 
 
@@ -81,16 +81,17 @@ def adapter_mix(x: torch.Tensor, a: torch.Tensor, w: float) -> torch.Tensor:
     """In place: x <- w * a * |x| / |a| + (1 - w) * x, norms over the last dim."""
     _need(x, torch.float32, "x"); _need(a, torch.float32, "a")
     rows, width = x.shape
-    check(_lib.load().aaclip_adapter_mix(ptr(x), ptr(a), w, rows, width, cur_stream()))
+    check(_lib.load().aaclip_adapter_mix(ptr(x), ptr(a), w, rows, width, cur_stream(x.device)))
     return x
 
 
 def anomaly_head(seg: Sequence[torch.Tensor], anchors: torch.Tensor, img_size: int, mode: int,
-                 det: Optional[torch.Tensor] = None, want_maps: bool = True):
+                 det: Optional[torch.Tensor] = None, want_maps: bool = True, want_extrema: bool = False):
     """seg: list of [B,P,E] (fp32 or bf16) normalised patch tokens; anchors fp32 [E,2] or [B,E,2].
 
     Returns (maps, scores): test modes maps fp32 [B,S,S] summed over levels; train mode [n_levels,B,2,S,S];
-    scores fp32 [B] if det is given, else None.
+    scores fp32 [B] if det is given, else None.  With `want_extrema` (test modes, shared anchors) a third value
+    fp32 [B,2] = per-image (min, max) of the maps, from the same kernel that writes them.
     """
     n = len(seg)
     if n == 0:
@@ -114,9 +115,16 @@ def anomaly_head(seg: Sequence[torch.Tensor], anchors: torch.Tensor, img_size: i
     if det is not None:
         _need(det, torch.float32, "det")
         scores = torch.empty(B, device=dev, dtype=torch.float32)
+    extrema = torch.empty(B, 2, device=dev, dtype=torch.float32) if want_extrema else None
+    lib = _lib.load()
+    # scratch comes from torch's caching allocator (stream-ordered, capturable); the library allocates nothing
+    ws_bytes = int(lib.aaclip_anomaly_head_workspace_bytes(n, B, P)) if want_maps else 0
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if ws_bytes else None
     arr = (C.c_void_p * n)(*[t.data_ptr() for t in seg])
-    check(_lib.load().aaclip_anomaly_head(arr, n, int(is_bf16), ptr(anchors), int(batched), ptr(det), B, P, E,
-                                          img_size, mode, ptr(maps), ptr(scores), cur_stream()))
+    check(lib.aaclip_anomaly_head(arr, n, int(is_bf16), ptr(anchors), int(batched), ptr(det), B, P, E, img_size, mode,
+                                  ptr(maps), ptr(scores), ptr(extrema), ptr(ws), ws_bytes, cur_stream(dev)))
+    if want_extrema:
+        return maps, scores, extrema
     return maps, scores
 
 
@@ -137,7 +145,7 @@ def preprocess_u8(images: torch.Tensor, size: int, mean=None, std=None) -> torch
     out = torch.empty(B, 3, size, size, device=images.device, dtype=torch.float32)
     m = (C.c_float * 3)(*mean) if mean is not None else None
     s = (C.c_float * 3)(*std) if std is not None else None
-    check(lib.aaclip_preprocess_u8(ptr(images), B, H0, W0, size, m, s, ptr(scratch), ptr(out), cur_stream()))
+    check(lib.aaclip_preprocess_u8(ptr(images), B, H0, W0, size, m, s, ptr(scratch), ptr(out), cur_stream(images.device)))
     return out
 
 
@@ -149,7 +157,7 @@ def resize_bicubic_u8(images: torch.Tensor, size: int) -> torch.Tensor:
     nbytes = int(lib.aaclip_preprocess_scratch_bytes(B, H0, W0, size))
     scratch = torch.empty(max(nbytes, 1), device=images.device, dtype=torch.uint8)
     out = torch.empty(B, size, size, 3, device=images.device, dtype=torch.uint8)
-    check(lib.aaclip_resize_bicubic_u8(ptr(images), B, H0, W0, size, ptr(scratch), ptr(out), cur_stream()))
+    check(lib.aaclip_resize_bicubic_u8(ptr(images), B, H0, W0, size, ptr(scratch), ptr(out), cur_stream(images.device)))
     return out
 
 
@@ -159,7 +167,7 @@ def map_minmax(maps: torch.Tensor) -> torch.Tensor:
     B = maps.shape[0]
     n_pix = maps.numel() // B if B else 0
     out = torch.empty(B, 2, device=maps.device, dtype=torch.float32)
-    check(_lib.load().aaclip_map_minmax(ptr(maps), B, n_pix, ptr(out), cur_stream()))
+    check(_lib.load().aaclip_map_minmax(ptr(maps), B, n_pix, ptr(out), cur_stream(maps.device)))
     return out
 
 
@@ -172,7 +180,7 @@ def fold_ln_weight(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.T
     colsum = torch.empty(N, device=w.device, dtype=torch.float32)
     bias_f = torch.empty(N, device=w.device, dtype=torch.float32)
     check(_lib.load().aaclip_fold_ln_weight(ptr(w), ptr(bias), ptr(gamma), ptr(beta), N, K, ptr(wf), ptr(colsum),
-                                            ptr(bias_f), cur_stream()))
+                                            ptr(bias_f), cur_stream(w.device)))
     return wf, colsum, bias_f
 
 
@@ -182,7 +190,7 @@ def rowstats_cast(x: torch.Tensor, slices: int):
     rows, width = x.shape
     xb = torch.empty(rows, width, device=x.device, dtype=torch.bfloat16)
     part = torch.empty(rows, slices, 2, device=x.device, dtype=torch.float32)
-    check(_lib.load().aaclip_rowstats_cast(ptr(x), rows, width, ptr(xb), ptr(part), slices, cur_stream()))
+    check(_lib.load().aaclip_rowstats_cast(ptr(x), rows, width, ptr(xb), ptr(part), slices, cur_stream(x.device)))
     return xb, part
 
 
@@ -194,7 +202,7 @@ def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
     part = torch.empty(M, N // 128, 2, device=a.device, dtype=torch.float32)
     check(_lib.load().aaclip_gemm_resid_ln(ptr(a), K, ptr(w), K, M, N, K, ptr(bias), ptr(x), N, ptr(xb), N, ptr(part),
-                                           cta_group, cur_stream()))
+                                           cta_group, cur_stream(a.device)))
     return xb, part
 
 
@@ -206,5 +214,5 @@ def gemm_lnfold(xb: torch.Tensor, wf: torch.Tensor, bias_f: torch.Tensor, colsum
     N = wf.shape[0]
     out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
     check(_lib.load().aaclip_gemm_lnfold(ptr(xb), K, ptr(wf), K, M, N, K, ptr(bias_f), ptr(colsum), ptr(part),
-                                         part.shape[1], eps, ptr(out), N, act, cta_group, cur_stream()))
+                                         part.shape[1], eps, ptr(out), N, act, cta_group, cur_stream(xb.device)))
     return out

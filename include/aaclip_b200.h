@@ -12,7 +12,10 @@
  *     owns only its packed weights and workspaces.
  *   - calls enqueue on `stream` and return 0 (AACLIP_OK) or a negative code; aaclip_last_error() returns the
  *     message for the calling thread.  There is no CPU fallback: without an sm_100 device calls fail.
- *   - one context per device; a context is not thread-safe.
+ *   - any number of contexts per process, on any devices; every call runs on its context's device and restores the
+ *     caller's current device before it returns.  A context is not thread-safe.
+ *   - ABI version 2 (aaclip_abi_version): v2 added seg_is_bf16 to aaclip_visual_forward, minmax_out to the fused
+ *     entries and minmax_out + a caller-owned workspace to aaclip_anomaly_head.
  */
 #ifndef AACLIP_B200_H_
 #define AACLIP_B200_H_
@@ -140,20 +143,28 @@ int aaclip_profile_read(aaclip_ctx* ctx, double* ms, long long* counts, int n_cl
 double aaclip_profile_span_ms(const aaclip_ctx* ctx);
 
 /* ---- AdaptedCLIP.forward (model/adapter.py:67-112) ------------------------------------------------- */
-/* image fp32 [B,3,S,S] (CLIP-normalised).  seg_out[i]: fp32 [B,P,E] L2-normalised patch tokens of level i
- * (or NULL to skip materialising them); det_out fp32 [B,E] (or NULL). */
-int aaclip_visual_forward(aaclip_ctx* ctx, const float* image, int B, float* const* seg_out, float* det_out,
-                          void* stream);
+/* image fp32 [B,3,S,S] (CLIP-normalised).  seg_out[i]: [B,P,E] L2-normalised patch tokens of level i, fp32 (the
+ * reference's dtype; seg_is_bf16 = 0) or bf16 (half the bytes for aaclip_anomaly_head to stream), or NULL to skip
+ * materialising them; det_out fp32 [B,E] (or NULL). */
+int aaclip_visual_forward(aaclip_ctx* ctx, const float* image, int B, void* const* seg_out, int seg_is_bf16,
+                          float* det_out, void* stream);
 
 /* ---- calculate_similarity_map + test.py:83-93 ------------------------------------------------------- */
-/* seg[i]: [B,P,E] fp32 (seg_is_bf16 = 0) or bf16 normalised patch tokens, n_levels of them; anchors fp32
- * [E,2] (anchors_batched = 0) or [B,E,2]; det fp32 [B,E] or NULL.
+/* seg[i]: [B,P,E] fp32 (seg_is_bf16 = 0) or bf16 normalised patch tokens, n_levels of them (1 = one
+ * calculate_similarity_map call, 4 = the whole test.py:89-93 loop); anchors fp32 [E,2] (anchors_batched = 0) or
+ * [B,E,2]; det fp32 [B,E] or NULL.
  * maps_out: test modes -> fp32 [B,S,S] = sum over levels of the per-level map (test.py:93);
  *           train mode -> fp32 [n_levels,B,2,S,S] softmaxed per level (forward_utils.py:214-215).
- * scores_out: fp32 [B] = ((det . anchors)[:,1] + 1)/2 (test.py:83-84) or NULL. */
+ * scores_out: fp32 [B] = ((det . anchors)[:,1] + 1)/2 (test.py:83-84) or NULL.
+ * minmax_out: fp32 [B,2] = per-image (min, max) of maps_out (test modes, shared anchors; what metrics_eval's
+ *           normalisation needs, forward_utils.py:241-252) or NULL.
+ * workspace: aaclip_anomaly_head_workspace_bytes(n_levels, B, P) bytes of 16-byte aligned device memory owned by the
+ *           caller (needed when maps_out != NULL): the call allocates nothing, never synchronises and is capturable. */
+long long aaclip_anomaly_head_workspace_bytes(int n_levels, int B, int P);
 int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors,
                         int anchors_batched, const float* det, int B, int P, int E, int img_size, int mode,
-                        float* maps_out, float* scores_out, void* stream);
+                        float* maps_out, float* scores_out, float* minmax_out, void* workspace,
+                        long long workspace_bytes, void* stream);
 
 /* Per-image extrema of anomaly maps: maps fp32 [B, n_pix] -> out fp32 [B][2] = (min, max).  The pixel-side input of
  * metrics_eval's image-level score (forward_utils.py:241-254: global min-max normalisation + per-image max); exact,
@@ -161,12 +172,15 @@ int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg_is_bf16, c
 int aaclip_map_minmax(const float* maps, int B, long long n_pix, float* out, void* stream);
 
 /* ---- fused image -> anomaly map (AdaptedCLIP.forward + head, no seg-token materialisation) ---------- */
+/* minmax_out: fp32 [B,2] per-image (min, max) of the maps, written by the head's epilogue (no second pass over the
+ * maps), or NULL. */
 int aaclip_forward_fused(aaclip_ctx* ctx, const float* image, int B, const float* anchors /*[E,2]*/, int mode,
-                         float* maps_out /*[B,S,S]*/, float* scores_out /*[B]*/, void* stream);
+                         float* maps_out /*[B,S,S]*/, float* scores_out /*[B]*/, float* minmax_out /*[B,2]*/,
+                         void* stream);
 /* Same with HOST buffers (pinned or pageable): H2D of the images, D2H of maps and scores, synchronous.
  * B > max_batch is processed in chunks through the two-slot pipeline below. */
 int aaclip_forward_fused_host(aaclip_ctx* ctx, const float* host_image, int B, const float* host_anchors, int mode,
-                              float* host_maps_out, float* host_scores_out);
+                              float* host_maps_out, float* host_scores_out, float* host_minmax_out /*[B,2] or NULL*/);
 
 /* Pipelined form of the host-buffer entry, for a loop over batches (test.py:get_predictions, test.py:53-99):
  * submit enqueues H2D (copy-in stream) -> forward (compute stream) -> D2H (copy-out stream) for one batch of
@@ -174,7 +188,8 @@ int aaclip_forward_fused_host(aaclip_ctx* ctx, const float* host_image, int B, c
  * the host buffers.  Two batches may be in flight, so the copies of neighbouring batches overlap the compute.
  * Host buffers must stay valid (and should be pinned) until the ticket has been waited for. */
 int aaclip_submit_host(aaclip_ctx* ctx, const float* host_image, int B, const float* host_anchors, int mode,
-                       float* host_maps_out, float* host_scores_out, long long* ticket);
+                       float* host_maps_out, float* host_scores_out, float* host_minmax_out /*[B,2] or NULL*/,
+                       long long* ticket);
 int aaclip_wait_host(aaclip_ctx* ctx, long long ticket);
 
 /* ---- loader-side image transform (dataset/__init__.py:127-136, :53-62) ------------------------------ */
@@ -193,7 +208,8 @@ int aaclip_resize_bicubic_u8(const uint8_t* images, int B, int H0, int W0, int S
 /* aaclip_submit_host with RAW images: host_u8 uint8 [B,H0,W0,3]; H2D of the bytes, transform on the device, then
  * the fused forward.  Same ticket / wait protocol (and the same two slots) as aaclip_submit_host. */
 int aaclip_submit_host_u8(aaclip_ctx* ctx, const uint8_t* host_u8, int B, int H0, int W0, const float* host_anchors,
-                          int mode, float* host_maps_out, float* host_scores_out, long long* ticket);
+                          int mode, float* host_maps_out, float* host_scores_out, float* host_minmax_out,
+                          long long* ticket);
 
 /* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
 /* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */

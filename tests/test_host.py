@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().aaclip_abi_version() == 1
+    assert _lib.load().aaclip_abi_version() == 2
 
 
 def test_cfg_struct_matches_header():
