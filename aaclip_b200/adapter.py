@@ -55,6 +55,12 @@ def _infer_cfg(clip_model, levels, image_adapt_until, text_adapt_until, i_w, t_w
     return ModelCfg(**kw)
 
 
+def effective_levels(levels, layers: int) -> List[int]:
+    """The taps the reference actually takes: block i is tapped when `i + 1 in self.levels` (model/adapter.py:100) -
+    membership semantics, so duplicates fire once, order is irrelevant and a level outside [1, layers] never fires."""
+    return [l for l in sorted({int(l) for l in levels}) if 1 <= l <= layers]
+
+
 class AdaptedCLIP(nn.Module):
     def __init__(
         self,
@@ -121,12 +127,9 @@ class AdaptedCLIP(nn.Module):
                                "move the model and its inputs to a cuda device")
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         if self._engine is None or self._engine.device != dev_index:
-            # the reference taps block i when `i + 1 in self.levels` (model/adapter.py:100): membership semantics, so
-            # duplicates fire once, order is irrelevant and a level outside [1, layers] never fires
-            levels = sorted({int(l) for l in self.levels})
-            cfg = _infer_cfg(self.clipmodel, levels, self.image_adapt_until, self.text_adapt_until, self.i_w,
+            cfg = _infer_cfg(self.clipmodel, list(self.levels), self.image_adapt_until, self.text_adapt_until, self.i_w,
                              self.t_w, self.relu)
-            cfg.levels = [l for l in levels if 1 <= l <= cfg.layers]
+            cfg.levels = effective_levels(self.levels, cfg.layers)
             if not cfg.levels:
                 raise ValueError(f"no level of {list(self.levels)} lies in [1, {cfg.layers}]: nothing to tap")
             self._engine = Engine(cfg, device=dev_index, max_batch=self.max_batch)

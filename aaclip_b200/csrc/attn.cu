@@ -557,15 +557,20 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
     case 2: v = pick<2>(minb, g_trace != nullptr, bal, ord); break;
     default: return host::fail(host::ERR_INVALID, "AACLIP_ATTN_POLY=%d out of range [0,2]", poly);
   }
-  static AttnKern configured[16] = {nullptr};
-  bool seen = false;
-  for (AttnKern kk : configured) seen = seen || (kk == v.fn);
-  if (!seen) {
-    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
-    for (AttnKern& kk : configured) if (!kk) { kk = v.fn; break; }
-  }
+  // the > 48 KB dynamic-smem opt-in is per (kernel, device context): remembered per device
   int dev = 0;
   AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
+  static AttnKern configured[64][4] = {{nullptr}};
+  bool seen = false;
+  if (dev >= 0 && dev < 64)
+    for (AttnKern kk : configured[dev]) seen = seen || (kk == v.fn);
+  if (!seen) {
+    AACLIP_CUDA_CHECK(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem));
+    if (dev >= 0 && dev < 64) {
+      bool stored = false;
+      for (AttnKern& kk : configured[dev]) if (!kk && !stored) { kk = v.fn; stored = true; }
+    }
+  }
   const int n_qt = (L + attn::BQ - 1) / attn::BQ;
   const long long items = (long long)n_qt * heads * B;
   if (items > INT_MAX) return host::fail(host::ERR_INVALID, "attention: %lld work items", items);

@@ -651,8 +651,8 @@ int fused_chunk(aaclip_ctx* c, const float* image, int nb, const float* anchors,
   TRY(visual_chunk(c, image, nb, nullptr, 0, 0, c->det, anchors, c->dots, st));
   // level sum -> blur -> upsample -> map rows, with the image's extrema and score from the same CTA
   if (maps || scores) {
-    RUN(PC_HEAD_MAPS, k::launch_maps_from_dots(c->dots, c->cfg.n_levels, nb, c->G, S, mode, c->det, anchors, c->E, maps, scores,
-                                               maps ? minmax : nullptr, st));
+    RUN(PC_HEAD_MAPS, k::launch_maps_from_dots(c->dots, nullptr, c->cfg.n_levels, nb, c->G, S, mode, c->det, anchors, c->E, maps,
+                                               scores, maps ? minmax : nullptr, false, st));
   }
   return host::OK;
 }

@@ -7,15 +7,19 @@
 
 namespace {
 
-template <int CG, int ACT, int OUT, int LNF = 0>
+template <int CG, int ACT, int OUT, int LNF = 0, int RV = 0>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD,
                const gemm::Args& args, int num_sms, cudaStream_t stream) {
-  using C = gemm::Cfg<CG, OUT == gemm::OUT_F32_RESID_LN>;
-  auto kern = gemm::gemm_kernel<CG, ACT, OUT, LNF>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  using C = gemm::Cfg<CG, OUT == gemm::OUT_F32_RESID_LN, RV>;
+  auto kern = gemm::gemm_kernel<CG, ACT, OUT, LNF, RV>;
+  // the opt-in to > 48 KB of dynamic shared memory belongs to the CURRENT device's context: remember it per
+  // (instantiation, device), so that a second context on another GPU of the same process is configured too
+  static bool configured[64] = {false};
+  int dev = 0;
+  AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     AACLIP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int tiles = ((args.M + C::BM * CG - 1) / (C::BM * CG)) * ((args.N + C::BN - 1) / C::BN);
   int clusters = num_sms / CG;
@@ -58,7 +62,14 @@ int dispatch(int act, int out_mode, const CUtensorMap& tmA, const CUtensorMap& t
   CASE(ACT_GELU_ERF, OUT_BF16)
   CASE(ACT_QUICK_GELU, OUT_BF16)
   CASE(ACT_NONE, OUT_F32_RESID)
-  CASE(ACT_NONE, OUT_F32_RESID_LN)
+  if (act == ACT_NONE && out_mode == OUT_F32_RESID_LN) {
+    // AACLIP_RLN_VARIANT=1 selects the round-1 epilogue (one x_old chunk in flight per warp) for A/B runs; the default
+    // (2) keeps a 3-deep x_old ring per warp.  Measured on B200 (tools/rln_probe.py, profiles/r2_rln_variants.txt):
+    // out_proj 98.8 vs 96.8 us alone, 2.67 vs 2.61 ms per step in the bench - the epilogue is not what bounds this GEMM.
+    static const int rv = getenv("AACLIP_RLN_VARIANT") ? atoi(getenv("AACLIP_RLN_VARIANT")) : 2;
+    if (rv == 1) return launch_one<CG, ACT_NONE, OUT_F32_RESID_LN, 0, 1>(tmA, tmB, tmC, tmD, a, sms, s);
+    return launch_one<CG, ACT_NONE, OUT_F32_RESID_LN, 0, 2>(tmA, tmB, tmC, tmD, a, sms, s);
+  }
   CASE(ACT_NONE, OUT_F32)
   CASE(ACT_LEAKY, OUT_F32)
   CASE(ACT_LEAKY, OUT_BF16)
@@ -112,10 +123,13 @@ int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N,
   a.M = M; a.N = N; a.K = K; a.bias = bias; a.out = out; a.ldo = ldo; a.pos = pos; a.P = P;
   a.anchors = anchors; a.partials = static_cast<float4*>(partials); a.dots_cols = dots_cols;
   a.ln_part = nullptr; a.ln_slices = 0; a.ln_width = K; a.ln_eps = 0.f; a.ln_colsum = nullptr; a.part_out = nullptr;
+  a.xb = nullptr; a.ldxb = 0;
   if (rln) {
-    rc = host::make_tmap_out(&tmD, ln->xb, M, N, ln->ldxb, true);
-    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(ln->xb) & 15u) != 0) return host::fail(host::ERR_INVALID, "gemm: xb must be 16-byte aligned");
     a.part_out = static_cast<float2*>(ln->part_out);
+    a.xb = static_cast<__nv_bfloat16*>(ln->xb); a.ldxb = ln->ldxb;
+    rc = host::make_tmap_out(&tmD, ln->xb, M, N, ln->ldxb, true);   // variants that stage the bf16 copy for a TMA store
+    if (rc) return rc;
   } else if (ln && ln->part_in) {
     a.ln_part = static_cast<const float2*>(ln->part_in);
     a.ln_slices = ln->slices; a.ln_eps = ln->eps; a.ln_colsum = ln->colsum;

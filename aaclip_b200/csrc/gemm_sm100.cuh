@@ -52,11 +52,16 @@ struct Args {
   float ln_eps;
   const float* ln_colsum; // s[N]
   // OUT_F32_RESID_LN (the PRODUCER): out <- out + acc + bias (fp32, in place through TMA load / store), plus the bf16
-  // copy of the new rows (tensor map tmD) and their per-slice partial sums
+  // copy of the new rows and their per-slice partial sums
   float2* part_out;       // [M][N / 128]
+  __nv_bfloat16* xb;      // [M][ldxb] bf16 copy of the new rows
+  int ldxb;
 };
 
-template <int CG, bool RLN = false>   // RLN: the OUT_F32_RESID_LN epilogue (8 KB of staging per warp, one stage fewer)
+// RLN: the OUT_F32_RESID_LN epilogue (64 KB of x_old ring, one stage fewer); RV selects its variant (see
+// epilogue_resid_ln): the working epilogue warps (8: two per TMEM lane quarter, 128 columns each; 4: one per quarter, all
+// 256 columns) and the depth of each warp's x_old ring.
+template <int CG, bool RLN = false, int RV = 0>
 struct Cfg {
   static constexpr int BM = 128;           // accumulator rows per CTA (== TMEM lanes)
   static constexpr int BN = 256;           // tile N (per CTA pair when CG == 2)
@@ -69,7 +74,11 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int NUM_EPI_WARPS = 8;
-  static constexpr int STAGING_BYTES = (RLN ? 2 : 1) * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled (RLN: X + Y)
+  // RLN: only 4 of the 8 epilogue warps work (one per TMEM lane quarter, all 256 columns of its 32 rows), each with a
+  // ring of XRING x_old chunks: what bounds that epilogue is bytes in flight per SM, not issue slots
+  static constexpr int ACTIVE_EPI_WARPS = (RLN && RV != 1 && RV != 4) ? 4 : 8;
+  static constexpr int XRING = RV == 1 ? 1 : RV == 2 ? 3 : RV == 4 ? 2 : 4;
+  static constexpr int STAGING_BYTES = (RLN ? 2 : 1) * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int THREADS = 128 + NUM_EPI_WARPS * 32;
@@ -297,16 +306,98 @@ __device__ __forceinline__ void epilogue_staged(uint32_t t_addr, uint8_t* stage,
   }
 }
 
-// OUT_F32_RESID_LN epilogue of one warp: 32 rows x 128 columns of  x_new = x_old + acc + bias  (lane == row).
-// x_old arrives by TMA load into X (4 KB, 128B-swizzled), is updated in place and leaves by TMA store; the bf16 copy
-// of x_new collects in Y (4 KB = 64 columns) and leaves every second chunk; the row's sum / sum of squares over the 128
-// columns go to part_out.  The next x_old chunk is requested as soon as the store has finished READING X.  (Pulling the
-// tile's x_old into L2 ahead of time - by these warps one tile ahead, or by the TMA producer late in the mainloop - was
-// measured 3-7 % SLOWER than no prefetch: out_proj 98.6 vs 102-105 us, c_proj 242 vs 249-253 us.)
+// OUT_F32_RESID_LN epilogue:  x_new = x_old + acc + bias  for one warp's 32 rows x (NCH * 32) columns of a tile
+// (lane == row), in chunks of 32 columns.  x_old is a 151 MB fp32 stream that lives in HBM: what bounds this epilogue is
+// how many of its bytes are in flight, so every warp keeps a RING of XR 4 KB chunks (128B-swizzled TMA boxes) that runs
+// XR - 1 chunks ahead of the arithmetic - across tile boundaries and ahead of the tile's accumulator (the loads do not
+// depend on it).  A chunk is updated in place and leaves by TMA store; its slot is refilled one chunk later, when that
+// store has finished reading it (cp.async.bulk.wait_group.read 1: does not wait in steady state).  The row's (sum, sum
+// of squares) per 128 columns go to part_out.  The bf16 copy of x_new leaves either straight from registers (YM 0: 4 x
+// 16 B, YM 1: 2 x 32 B per lane and chunk) or through a 4 KB staging buffer and a TMA store every second chunk (YM 2).
+// History: one chunk in flight per warp (8 warps x 8 KB: x chunk + bf16 staging; kept as epilogue_resid_ln_v0) made
+// every chunk pay a full HBM round trip: out_proj 110 us in-step against a 70 us HBM floor, DRAM 54 % busy.
+template <int NCH, int XR, int YM, typename RequestFn, typename ArriveFn>
+__device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* xring, uint64_t* xbar, uint32_t& j,
+                                                  RequestFn&& request, const CUtensorMap* tmC, const CUtensorMap* tmD,
+                                                  int row0, int col0, uint32_t lane, const Args& a, ArriveFn&& release_tmem) {
+  const uint32_t sw = lane & 7u;
+  const int row = row0 + int(lane);
+  [[maybe_unused]] uint8_t* Y = xring + XR * 4096;
+  [[maybe_unused]] uint8_t* yrow = Y + lane * 128;
+  float sum = 0.f, ssq = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c, ++j) {
+    const int col = col0 + c * 32;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(t_addr + c * 32, v);
+    ptx::tmem_ld_wait();
+    if (c == NCH - 1) release_tmem();
+    float f[32];
+    bias_act32<ACT_NONE>(v, f, a.bias, col);
+    const uint32_t slot = j % uint32_t(XR);
+    uint8_t* X = xring + slot * 4096;
+    uint8_t* xrow = X + lane * 128;
+    ptx::mbar_wait(&xbar[slot], (j / uint32_t(XR)) & 1u);   // x_old chunk j has landed (rows >= M: TMA zero fill)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float o0, o1, o2, o3;
+      ptx::ld_shared_v4(xrow + ((uint32_t(q) ^ sw) << 4), o0, o1, o2, o3);
+      f[4 * q + 0] += o0; f[4 * q + 1] += o1; f[4 * q + 2] += o2; f[4 * q + 3] += o3;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { sum += f[i]; ssq = fmaf(f[i], f[i], ssq); }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      ptx::st_shared_v4(xrow + ((uint32_t(q) ^ sw) << 4), __float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
+                        __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
+    uint32_t h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = ptx::pack_bf16x2(f[2 * i], f[2 * i + 1]);
+    if constexpr (YM == 2) {
+      if ((c & 1) == 0) {   // the previous pair's Y store (in the group committed one chunk ago) must have read Y
+        if (lane == 0) ptx::bulk_wait_read<0>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        ptx::st_shared_v4(yrow + ((uint32_t((c & 1) * 4 + q) ^ sw) << 4), h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    } else if (row < a.M) {
+      __nv_bfloat16* o = a.xb + size_t(row) * a.ldxb + col;
+      if constexpr (YM == 1) {   // two full 32-byte sectors per lane
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 16 * q), "r"(h[8 * q]),
+                       "r"(h[8 * q + 1]), "r"(h[8 * q + 2]), "r"(h[8 * q + 3]), "r"(h[8 * q + 4]), "r"(h[8 * q + 5]),
+                       "r"(h[8 * q + 6]), "r"(h[8 * q + 7]) : "memory");
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<uint4*>(o)[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (row0 < a.M) {   // rows past M are clipped by the TMA unit
+        ptx::tma_store_2d(tmC, X, col, row0);
+        if constexpr (YM == 2) { if (c & 1) ptx::tma_store_2d(tmD, Y, col - 32, row0); }
+      }
+      ptx::bulk_commit();
+      if (j >= 1) ptx::bulk_wait_read<1>();   // the store of chunk j - 1 has finished reading slot (j + XR - 1) % XR
+      request(j + uint32_t(XR) - 1u);
+    }
+    if ((c & 3) == 3) {
+      if (row < a.M) a.part_out[size_t(row) * (a.N >> 7) + (col >> 7)] = make_float2(sum, ssq);
+      sum = 0.f; ssq = 0.f;
+    }
+  }
+}
+
+// Round-1 form (RV 1), kept for A/B: 8 warps x 128 columns, ONE x_old chunk in flight per warp (X 4 KB + bf16 staging Y 4 KB).
 template <typename ArriveFn>
-__device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stage, uint64_t* xbar, uint32_t& xphase,
-                                                  const CUtensorMap* tmC, const CUtensorMap* tmD, int row0, int col0,
-                                                  uint32_t lane, const Args& a, ArriveFn&& release_tmem) {
+__device__ __forceinline__ void epilogue_resid_ln_v0(uint32_t t_addr, uint8_t* stage, uint64_t* xbar, uint32_t& xphase,
+                                                     const CUtensorMap* tmC, const CUtensorMap* tmD, int row0, int col0,
+                                                     uint32_t lane, const Args& a, ArriveFn&& release_tmem) {
   uint8_t* X = stage;
   uint8_t* Y = stage + 4096;
   uint8_t* xrow = X + lane * 128;
@@ -314,7 +405,6 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
   const uint32_t sw = lane & 7u;
   const bool active = row0 < a.M;   // warp-uniform
   float sum = 0.f, ssq = 0.f;
-  // (the caller requested x_old chunk 0 before it waited for the accumulator: resid_ln_request_first)
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const int col = col0 + c * 32;
@@ -324,7 +414,7 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
     if (c == 3) release_tmem();
     float f[32];
     bias_act32<ACT_NONE>(v, f, a.bias, col);
-    if (active) { ptx::mbar_wait(xbar, xphase); xphase ^= 1u; }   // x_old chunk c has landed (rows >= M: zero fill)
+    if (active) { ptx::mbar_wait(xbar, xphase); xphase ^= 1u; }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float o0, o1, o2, o3;
@@ -332,12 +422,11 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
       f[4 * q + 0] += o0; f[4 * q + 1] += o1; f[4 * q + 2] += o2; f[4 * q + 3] += o3;
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { sum += f[j]; ssq = fmaf(f[j], f[j], ssq); }
+    for (int i = 0; i < 32; ++i) { sum += f[i]; ssq = fmaf(f[i], f[i], ssq); }
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       ptx::st_shared_v4(xrow + ((uint32_t(q) ^ sw) << 4), __float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]),
                         __float_as_uint(f[4 * q + 2]), __float_as_uint(f[4 * q + 3]));
-    // Y is free: at c == 0 by the wait above, at c == 2 by the wait that preceded this chunk's x_old request
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       ptx::st_shared_v4(yrow + ((uint32_t((c & 1) * 4 + q) ^ sw) << 4), ptx::pack_bf16x2(f[8 * q], f[8 * q + 1]),
@@ -352,7 +441,7 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
       }
       ptx::bulk_commit();
       if (c < 3) {
-        ptx::bulk_wait_read<0>();    // X (and Y) have been read: X may take the next x_old chunk
+        ptx::bulk_wait_read<0>();
         if (active) {
           ptx::mbar_arrive_expect_tx(xbar, 4096);
           ptx::tma_load_2d(X, tmC, xbar, col + 32, row0);
@@ -364,12 +453,10 @@ __device__ __forceinline__ void epilogue_resid_ln(uint32_t t_addr, uint8_t* stag
   const int row = row0 + int(lane);
   if (row < a.M) a.part_out[size_t(row) * (a.N >> 7) + (col0 >> 7)] = make_float2(sum, ssq);
 }
-
-// First x_old chunk of a tile, requested BEFORE the warp waits for the tile's accumulator (hides one round trip).
 __device__ __forceinline__ void resid_ln_request_first(uint8_t* stage, uint64_t* xbar, const CUtensorMap* tmC, int row0,
                                                        int col0, uint32_t lane, const Args& a) {
   if (lane == 0) {
-    ptx::bulk_wait_read<0>();        // the previous tile's stores have finished reading X and Y
+    ptx::bulk_wait_read<0>();
     if (row0 < a.M) {
       ptx::mbar_arrive_expect_tx(xbar, 4096);
       ptx::tma_load_2d(stage, tmC, xbar, col0, row0);
@@ -404,11 +491,11 @@ __device__ __forceinline__ void epilogue_dots(uint32_t t_addr, int row0, int col
   if (row < a.M) a.partials[size_t(row) * (a.dots_cols >> 7) + (col0 >> 7)] = make_float4(ss, d0, d1, 0.f);
 }
 
-template <int CG, int ACT, int OUT, int LNF = 0>
+template <int CG, int ACT, int OUT, int LNF = 0, int RV = 0>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const Args args) {
-  using C = Cfg<CG, OUT == OUT_F32_RESID_LN>;
+  using C = Cfg<CG, OUT == OUT_F32_RESID_LN, RV>;
   extern __shared__ uint8_t smem_raw[];
   // identical offset in both CTAs of a pair: the dynamic smem window starts at the same address
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -421,7 +508,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint64_t* xbar = tempty + 3;   // OUT_F32_RESID_LN: one x_old barrier per epilogue warp
+  uint64_t* xbar = tempty + 3;   // OUT_F32_RESID_LN: XRING x_old barriers per working epilogue warp
+  static_assert((2 * C::STAGES + 4 + 1 + C::ACTIVE_EPI_WARPS * C::XRING) * 8 <= C::BAR_BYTES || OUT != OUT_F32_RESID_LN,
+                "barrier block too small");
 
   const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t lane = ptx::lane_id();
@@ -442,7 +531,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     if constexpr (OUT != OUT_F32_PATCH) ptx::prefetch_tmap(&tmC);
-    if constexpr (OUT == OUT_F32_RESID_LN) ptx::prefetch_tmap(&tmD);
+    if constexpr (OUT == OUT_F32_RESID_LN && (RV == 1 || RV == 2)) ptx::prefetch_tmap(&tmD);
   }
   if (warp == 9 && ptx::elect_one()) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -451,10 +540,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);                          // tcgen05.commit
-      ptx::mbar_init(&tempty[a], CG * C::NUM_EPI_WARPS);     // one arrive per epilogue warp of the pair
+      ptx::mbar_init(&tempty[a], CG * C::ACTIVE_EPI_WARPS);  // one arrive per working epilogue warp of the pair
     }
     if constexpr (OUT == OUT_F32_RESID_LN)
-      for (int w = 0; w < C::NUM_EPI_WARPS; ++w) ptx::mbar_init(&xbar[w], 1);
+      for (int w = 0; w < C::ACTIVE_EPI_WARPS * C::XRING; ++w) ptx::mbar_init(&xbar[w], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 10) {
@@ -520,19 +609,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (CG == 1) ptx::mma_commit(&tfull[acc]); else ptx::mma_commit_cg2(&tfull[acc], 0x3);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < uint32_t(C::ACTIVE_EPI_WARPS)) {
     // ===================================================== epilogue: TMEM -> regs -> (smem -> TMA | global)
     const uint32_t q = warp & 3u;            // TMEM lane quarter this warp may read
-    const uint32_t half = warp >> 2;         // which 128 accumulator columns
-    uint8_t* stage = staging + warp * C::STAGING_BYTES;
+    const uint32_t half = warp >> 2;         // which 128 accumulator columns (RLN: 0 - the warp takes all 256)
+    uint8_t* stage = staging + warp * (C::NUM_EPI_WARPS / C::ACTIVE_EPI_WARPS) * C::STAGING_BYTES;
     uint32_t it = 0;
-    [[maybe_unused]] uint32_t xphase = 0;
+    // RLN: x_old chunk jj of this warp's chunk stream (NCH per tile, tiles in this CTA's order) -> ring slot jj % XRING
+    constexpr int NCH = 32 / C::ACTIVE_EPI_WARPS;   // 32-column chunks per warp and tile: 8 (4 warps) / 4 (8 warps)
+    [[maybe_unused]] uint32_t xj = 0, xphase = 0;
+    [[maybe_unused]] uint64_t* xb = &xbar[warp * C::XRING];
+    [[maybe_unused]] auto request_x = [&](uint32_t jj) {
+      const int t = cluster_id + int(jj / uint32_t(NCH)) * num_clusters;
+      if (t >= num_tiles) return;
+      const int mb = t / tiles_n, nb = t - mb * tiles_n;
+      const uint32_t slot = jj % uint32_t(C::XRING);
+      ptx::mbar_arrive_expect_tx(&xb[slot], 4096);
+      ptx::tma_load_2d(stage + slot * 4096, &tmC, &xb[slot], nb * C::BN + int(half) * 128 + int(jj % uint32_t(NCH)) * 32,
+                       mb * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u));
+    };
+    if constexpr (OUT == OUT_F32_RESID_LN && RV != 1) {
+      if (lane == 0) for (uint32_t jj = 0; jj + 1 < uint32_t(C::XRING); ++jj) request_x(jj);
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       const int row0 = m_blk * C::BM * CG + int(cta_rank) * C::BM + int(q * 32u);
-      if constexpr (OUT == OUT_F32_RESID_LN)
-        resid_ln_request_first(stage, &xbar[warp], &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args);
+      if constexpr (OUT == OUT_F32_RESID_LN && RV == 1)
+        resid_ln_request_first(stage, xb, &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args);
       ptx::mbar_wait(&tfull[acc], aph);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((q * 32u) << 16) + acc * C::BN + half * 128u;
@@ -558,8 +662,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (col0 < args.dots_cols) epilogue_dots<ACT>(t_addr, row0, col0, lane, args, release_tmem);
         else epilogue_staged<ACT, OUT_F32>(t_addr, stage, &tmC, row0, col0, lane, args, release_tmem);
       } else if constexpr (OUT == OUT_F32_RESID_LN) {
-        epilogue_resid_ln(t_addr, stage, &xbar[warp], xphase, &tmC, &tmD, row0, n_blk * C::BN + int(half) * 128, lane,
-                          args, release_tmem);
+        if constexpr (RV == 1)
+          epilogue_resid_ln_v0(t_addr, stage, xb, xphase, &tmC, &tmD, row0, n_blk * C::BN + int(half) * 128, lane, args,
+                               release_tmem);
+        else
+          epilogue_resid_ln<NCH, C::XRING, (RV == 2) ? 2 : (RV == 0) ? 0 : 1>(
+              t_addr, stage, xb, xj, request_x, &tmC, &tmD, row0, n_blk * C::BN + int(half) * 128, lane, args, release_tmem);
       } else {
         epilogue_staged<ACT, OUT, LNF>(t_addr, stage, &tmC, row0, n_blk * C::BN + int(half) * 128, lane, args,
                                        release_tmem);

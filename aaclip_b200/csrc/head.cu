@@ -204,29 +204,86 @@ head_maps_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int
   }
 }
 
-// ---- fused engine path, test modes: dots [n_levels][B*P][2] (left by the seg_proj GEMM epilogue + dots_finish) ->
-// level-summed patch map -> blur -> upsample -> map rows, extrema, image score.  One CTA (8 warps) per image.
+// ---- test-mode image tails: per-patch scalars -> blur -> upsample -> map rows, extrema, image score.
+// Input: either dots [n_levels][B*P][2] (fused engine path: left by the seg_proj GEMM epilogue + dots_finish; the level
+// sum (s1 + 1 - s0) / 2 is formed here) or msum [B][P] (already level-summed: head_stream_kernel).  A cluster of R CTAs
+// (8 warps each) shares one image: every CTA blurs the tiny G x G map itself and writes 1/R of the output rows; the
+// cluster's extrema meet in rank 0 through distributed shared memory.  R = 1 when the batch alone fills the SMs.
 __global__ void __launch_bounds__(headepi::THREADS)
-maps_from_dots_kernel(const float* __restrict__ dots, int n_levels, int B, int G, int S, int ksize, float sigma,
-                      const float* __restrict__ det, const float* __restrict__ anchors, int E, float* __restrict__ maps,
-                      float* __restrict__ scores, float* __restrict__ minmax) {
+maps_from_dots_kernel(const float* __restrict__ dots, const float* __restrict__ msum, int n_levels, int B, int G, int S,
+                      int ksize, const headepi::Taps taps, int R, const float* __restrict__ det, const float* __restrict__ anchors, int E,
+                      float* __restrict__ maps, float* __restrict__ scores, float* __restrict__ minmax) {
   extern __shared__ __align__(16) float epi_sm[];
-  const int P = G * G, b = blockIdx.x, tid = threadIdx.x;
+  __shared__ __align__(8) float cl_red[2 * 8];   // rank 0: the cluster's partial (min, max) pairs
+  const int P = G * G, tid = threadIdx.x;
+  const int b = blockIdx.x / R, rank = blockIdx.x - b * R;
   const headepi::Smem e = headepi::carve(epi_sm, P, G, S);
-  headepi::setup(e, tid, headepi::THREADS, G, S, ksize, sigma);
-  ptx::grid_dep_sync();
+  headepi::setup(e, tid, headepi::THREADS, G, S, ksize, taps);
+  ptx::grid_dep_sync();   // everything above overlapped the producing kernel's tail (programmatic dependent launch)
   const size_t rows = (size_t)B * P;
-  for (int i = tid; i < P; i += headepi::THREADS) {
-    float acc = 0.f;
-    for (int l = 0; l < n_levels; ++l) {
-      const float2 d = *reinterpret_cast<const float2*>(dots + ((size_t)l * rows + (size_t)b * P + i) * 2);
-      acc += (100.0f * d.y + 1.0f - 100.0f * d.x) * 0.5f;   // per level exactly as the reference (test.py:85)
+  for (int i0 = tid; i0 < P; i0 += 4 * headepi::THREADS) {
+    // four patches x all levels per thread with every load issued before the first use: the inputs are cold (HBM / L2
+    // round trips of a microsecond each), a dependent chain of n_levels * P / 256 of them would dominate the kernel
+    if (msum != nullptr) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * headepi::THREADS;
+        v[q] = (i < P) ? __ldcg(msum + (size_t)b * P + i) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * headepi::THREADS;
+        if (i < P) e.m[i] = v[q];
+      }
+    } else {
+      float2 d[4][MAX_LEVELS];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * headepi::THREADS;
+#pragma unroll
+        for (int l = 0; l < MAX_LEVELS; ++l)
+          d[q][l] = (i < P && l < n_levels) ? __ldg(reinterpret_cast<const float2*>(dots + ((size_t)l * rows + (size_t)b * P + i) * 2))
+                                            : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * headepi::THREADS;
+        float acc = 0.f;
+#pragma unroll
+        for (int l = 0; l < MAX_LEVELS; ++l)
+          if (l < n_levels) acc += (100.0f * d[q][l].y + 1.0f - 100.0f * d[q][l].x) * 0.5f;   // per level as the reference (test.py:85)
+        if (i < P) e.m[i] = acc;
+      }
     }
-    e.m[i] = acc;
   }
-  if (tid < 32 && scores != nullptr) headepi::image_score(det, anchors, E, b, tid, scores);
+  if (rank == 0 && tid < 32 && scores != nullptr) {
+    if (E == 768) headepi::image_score_unrolled<24>(det, anchors, b, tid, scores);
+    else headepi::image_score(det, anchors, E, b, tid, scores);
+  }
   __syncthreads();
-  if (maps != nullptr) headepi::image(e, tid, b, G, S, ksize, maps, minmax, [] { __syncthreads(); });
+  if (maps == nullptr) return;   // uniform over the cluster
+  const int rows_per = (S + R - 1) / R;
+  const int y0 = min(S, rank * rows_per), y1 = min(S, y0 + rows_per);
+  float lo, hi;
+  headepi::image(e, tid, b, G, S, ksize, y0, y1, maps, lo, hi, [] { __syncthreads(); });
+  if (minmax == nullptr) return;
+  headepi::block_minmax(e, tid, lo, hi, [] { __syncthreads(); });
+  if (R == 1) {
+    if (tid == 0) { minmax[2 * b] = lo; minmax[2 * b + 1] = hi; }
+    return;
+  }
+  if (tid == 0) {   // my (min, max) -> rank 0's cl_red[rank]
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(&cl_red[2 * rank])), "r"(0));
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(lo), "f"(hi) : "memory");
+  }
+  ptx::cluster_sync();   // release / acquire: every partial has landed in rank 0's shared memory
+  if (rank == 0 && tid == 0) {
+    for (int r = 1; r < R; ++r) { lo = fminf(lo, cl_red[2 * r]); hi = fmaxf(hi, cl_red[2 * r + 1]); }
+    minmax[2 * b] = lo;
+    minmax[2 * b + 1] = hi;
+  }
 }
 
 // scores[b] = (<det[b], anchors[:,1]> + 1) / 2      (test.py:83-84)
@@ -314,9 +371,10 @@ int k::launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_
   return host::OK;
 }
 
-// Test modes from precomputed dots: level sum -> blur -> upsample -> maps (+ extrema, + image scores), one launch.
-int k::launch_maps_from_dots(const float* dots, int n_levels, int B, int G, int S, int mode, const float* det,
-                             const float* anchors, int E, float* maps, float* scores, float* minmax,
+// Test modes from precomputed dots (or level-summed scalars `msum`): blur -> upsample -> maps (+ extrema, + image
+// scores), one launch.  pdl: chain to the preceding kernel of the stream by programmatic dependent launch.
+int k::launch_maps_from_dots(const float* dots, const float* msum, int n_levels, int B, int G, int S, int mode, const float* det,
+                             const float* anchors, int E, float* maps, float* scores, float* minmax, bool pdl,
                              cudaStream_t stream) {
   if (B <= 0) return host::OK;
   if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
@@ -325,13 +383,45 @@ int k::launch_maps_from_dots(const float* dots, int n_levels, int B, int G, int 
   if (G <= pad) return host::fail(host::ERR_INVALID, "head: grid %d too small for reflect padding %d", G, pad);
   if (scores != nullptr && (det == nullptr || anchors == nullptr))
     return host::fail(host::ERR_INVALID, "head: scores requested without det / anchors");
+  if ((dots == nullptr) == (msum == nullptr)) return host::fail(host::ERR_INVALID, "head: exactly one of dots / msum");
+  if (n_levels < 1 || n_levels > MAX_LEVELS) return host::fail(host::ERR_INVALID, "head: n_levels=%d", n_levels);
   const size_t smem = headepi::smem_floats(G * G, G, S) * sizeof(float);
   if (smem > 200 * 1024) return host::fail(host::ERR_INVALID, "head: img_size %d / grid %d needs %zu B smem", S, G, smem);
   if (smem > 48 * 1024)
     AACLIP_CUDA_CHECK(cudaFuncSetAttribute(maps_from_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  AACLIP_CUDA_CHECK(host::launch(maps_from_dots_kernel, dim3(B), dim3(headepi::THREADS), smem, stream, dots, n_levels, B, G, S,
-                                 pad * 2 + 1, mode == AACLIP_HEAD_TEST_INDUSTRIAL ? 1.0f : 1.5f, det, anchors, E, maps, scores,
-                                 minmax));
+  int dev = 0;
+  AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
+  const int sms = host::sm_count(dev) > 0 ? host::sm_count(dev) : 148;
+  // rows of one image over a cluster of R CTAs while the batch alone does not fill the SMs
+  // the tail is latency bound (8 warps per CTA, short dependent chains), not store bound: split an image's rows over
+  // R CTAs while that keeps the grid within ~2 CTAs per SM (measured at batch 64: R = 1 / 2 / 4 / 8 -> 67.7 / 59.3 /
+  // 55.0 / 68.8 us for the whole head; every CTA repeats the table set-up, the gather and the blur)
+  int R = 1;
+  while (maps != nullptr && R < 4 && 2 * R * B <= 2 * sms) R *= 2;
+  if (getenv("AACLIP_HEAD_R")) R = std::max(1, std::min(8, atoi(getenv("AACLIP_HEAD_R"))));   // diagnostics
+  if (getenv("AACLIP_HEAD_NOPDL")) pdl = false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * R);
+  cfg.blockDim = dim3(headepi::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (R > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = R; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl || host::pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const headepi::Taps taps = headepi::gaussian_taps(pad * 2 + 1, mode == AACLIP_HEAD_TEST_INDUSTRIAL ? 1.0f : 1.5f);
+  AACLIP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, maps_from_dots_kernel, dots, msum, n_levels, B, G, S, pad * 2 + 1, taps, R, det,
+                                       anchors, E, maps, scores, minmax));
   return host::OK;
 }
 
@@ -362,6 +452,9 @@ extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg
   while ((G + 1) * (G + 1) <= P) ++G;  // H = int(sqrt(L)), forward_utils.py:201
   if (G * G != P) return host::fail(host::ERR_INVALID, "head: P=%d is not a square grid", P);
   if (scores_out != nullptr && det == nullptr) return host::fail(host::ERR_INVALID, "head: scores requested without det");
+  for (int l = 0; l < n_levels; ++l)
+    if (seg[l] == nullptr || (reinterpret_cast<uintptr_t>(seg[l]) & 15u) != 0)
+      return host::fail(host::ERR_INVALID, "head: seg[%d] must be a 16-byte aligned device pointer", l);
   const bool test_mode = (mode == AACLIP_HEAD_TEST_INDUSTRIAL || mode == AACLIP_HEAD_TEST_MEDICAL);
   if (minmax_out != nullptr && (!test_mode || maps_out == nullptr))
     return host::fail(host::ERR_INVALID, "head: extrema are produced with the test-mode maps only");
@@ -370,16 +463,20 @@ extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg
         (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
       return host::fail(host::ERR_INVALID, "head: workspace of %lld bytes (16-byte aligned) required, got %lld",
                         aaclip_anomaly_head_workspace_bytes(n_levels, B, P), workspace_bytes);
-    if (k::head_stream_supported(n_levels, seg_is_bf16, anchors_batched, E, P, G, img_size, mode, seg))
-      // the whole head in one launch (head_stream.cu): tokens streamed once, maps + extrema + scores written once
-      return k::launch_head_stream(seg, n_levels, seg_is_bf16, anchors, det, B, P, G, img_size, mode, maps_out, scores_out,
-                                   minmax_out, workspace, stream);
+    if (k::head_stream_supported(n_levels, seg_is_bf16, anchors_batched, E, P, G, img_size, mode, seg)) {
+      // tokens streamed once (head_stream.cu: one scalar per patch + the image scores), then the image tails, chained
+      // by programmatic dependent launch: maps + extrema written once
+      int rc = k::launch_head_stream(seg, n_levels, seg_is_bf16, anchors, det, B, P, scores_out, workspace, stream);
+      if (rc) return rc;
+      return k::launch_maps_from_dots(nullptr, static_cast<const float*>(workspace), n_levels, B, G, img_size, mode, nullptr,
+                                      nullptr, E, maps_out, nullptr, minmax_out, true, stream);
+    }
     float* dots = static_cast<float*>(workspace);
     int rc = k::launch_patch_dots(seg, n_levels, seg_is_bf16, anchors, anchors_batched, B, P, E, dots, stream);
     if (rc) return rc;
     if (test_mode && !anchors_batched)
-      return k::launch_maps_from_dots(dots, n_levels, B, G, img_size, mode, det, anchors, E, maps_out, scores_out, minmax_out,
-                                      stream);
+      return k::launch_maps_from_dots(dots, nullptr, n_levels, B, G, img_size, mode, det, anchors, E, maps_out, scores_out,
+                                      minmax_out, false, stream);
     if (minmax_out != nullptr) return host::fail(host::ERR_INVALID, "head: extrema need shared anchors");
     rc = k::launch_head_maps(dots, B, G, img_size, mode, n_levels, maps_out, stream);
     if (rc) return rc;

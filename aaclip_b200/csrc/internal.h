@@ -75,18 +75,20 @@ int launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, con
 int launch_head_maps(const float* dots, int B, int G, int S, int mode, int n_levels, float* maps, cudaStream_t stream);
 int launch_scores(const float* det, const float* anchors, int anchors_batched, int B, int E, float* scores,
                   cudaStream_t stream);
-// test modes from dots [n_levels][B*P][2]: level sum -> blur -> upsample -> maps [B,S,S] (+ minmax [B,2], + scores [B]
-// from det / anchors); any of maps / scores / minmax may be null.  One CTA per image (head_epilogue.cuh).
-int launch_maps_from_dots(const float* dots, int n_levels, int B, int G, int S, int mode, const float* det,
-                          const float* anchors, int E, float* maps, float* scores, float* minmax, cudaStream_t stream);
-// The A7 contract as one persistent streaming kernel (head_stream.cu): test modes, shared anchors, E = 768, bf16 or
-// fp32 tokens, 16-byte aligned level pointers.  workspace: head_stream_workspace_bytes(B, P) bytes of device memory.
+// test modes from dots [n_levels][B*P][2] (level sum formed here) or msum [B][P] (already level-summed): blur ->
+// upsample -> maps [B,S,S] (+ minmax [B,2], + scores [B] from det / anchors); any of maps / scores / minmax may be null.
+// A cluster of 1, 2 or 4 CTAs per image (head_epilogue.cuh); pdl chains it to the stream's previous kernel.
+int launch_maps_from_dots(const float* dots, const float* msum, int n_levels, int B, int G, int S, int mode, const float* det,
+                          const float* anchors, int E, float* maps, float* scores, float* minmax, bool pdl,
+                          cudaStream_t stream);
+// The token-streaming half of the A7 contract (head_stream.cu): test modes, shared anchors, E = 768, bf16 or fp32
+// tokens, 16-byte aligned level pointers -> level-summed scalars [B, P] at the start of `workspace`
+// (head_stream_workspace_bytes(B, P) bytes) and scores [B].
 long long head_stream_workspace_bytes(int B, int P);
 bool head_stream_supported(int n_levels, int seg_is_bf16, int anchors_batched, int E, int P, int G, int S, int mode,
                            const void* const* seg);
 int launch_head_stream(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors, const float* det,
-                       int B, int P, int G, int S, int mode, float* maps, float* scores, float* minmax, void* workspace,
-                       cudaStream_t stream);
+                       int B, int P, float* scores, void* workspace, cudaStream_t stream);
 
 // Loader-side transform (dataset/__init__.py:127-136): u8 [B,H0,W0,3] -> PIL-bicubic resize -> /255 -> normalise ->
 // fp32 [B,3,S,S]; scratch: 3*B*H0*S bytes (unused when W0 == S); mean/std: host float[3] or null (CLIP constants).

@@ -107,6 +107,8 @@ def anomaly_head(seg: Sequence[torch.Tensor], anchors: torch.Tensor, img_size: i
     if tuple(anchors.shape) != ((B, E, 2) if batched else (E, 2)):
         raise ValueError(f"anchors shape {tuple(anchors.shape)}")
     dev = seg[0].device
+    # the kernels read tokens with 16-byte vector / bulk loads: a view at an odd offset into a larger buffer is re-packed
+    seg = [t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format) for t in seg]
     maps = None
     if want_maps:
         shape = (n, B, 2, img_size, img_size) if mode == HEAD_TRAIN_SOFTMAX else (B, img_size, img_size)

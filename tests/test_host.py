@@ -132,7 +132,11 @@ def _gloo_worker(rank, world, total, port, q):
     full = torch.arange(total, dtype=torch.float32) * 0.5 + 1
     b, e = shard_range(total, rank, world)
     out = gather_scores(full[b:e].clone(), total)
-    q.put((rank, bool(torch.equal(out, full))))
+    ok = bool(torch.equal(out, full))
+    if total % world == 0:   # even shards: one collective straight into a caller-owned buffer
+        buf = torch.empty(total)
+        ok = ok and gather_scores(full[b:e].clone(), total, out=buf) is buf and bool(torch.equal(buf, full))
+    q.put((rank, ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -202,3 +206,37 @@ def test_new_entry_points_argument_checks_without_gpu():
     assert b"256" in lib.aaclip_last_error()                                                 # N % 256 != 0
     assert lib.aaclip_gemm_lnfold(buf, 64, buf, 64, 128, 256, 64, None, None, out, 8, 1e-5, buf, 256, 0, 2, None) == -1
     assert b"colsum" in lib.aaclip_last_error()
+
+
+def test_head_workspace_contract_without_gpu():
+    """aaclip_anomaly_head takes its scratch from the caller (no allocation, no global state inside the library): the
+    size query and the argument errors are host-side and run without a device."""
+    import ctypes as C
+    from aaclip_b200 import _lib
+    lib = _lib.load()
+    need = lib.aaclip_anomaly_head_workspace_bytes(4, 64, 576)
+    assert need >= 4 * 64 * 576 * 2 * 4                      # the general form's dots [levels][B*P][2]
+    assert lib.aaclip_anomaly_head_workspace_bytes(1, 64, 576) >= (64 * 576 + 64) * 4   # streaming form: scalars + counters
+    assert lib.aaclip_anomaly_head_workspace_bytes(0, 1, 1) == 0
+    seg = (C.c_void_p * 1)(0x1000)
+    f = (C.c_float * 4)()
+    # empty batch: no-op;  maps without workspace, non-square grid, extrema without maps: ERR_INVALID
+    assert lib.aaclip_anomaly_head(seg, 1, 0, f, 0, None, 0, 576, 768, 336, 0, f, None, None, None, 0, None) == 0
+    assert lib.aaclip_anomaly_head(seg, 1, 0, f, 0, None, 2, 576, 768, 336, 0, f, None, None, None, 0, None) == -1
+    assert b"workspace" in lib.aaclip_last_error()
+    assert lib.aaclip_anomaly_head(seg, 1, 0, f, 0, None, 2, 577, 768, 336, 0, f, None, None, f, need, None) == -1
+    assert b"square" in lib.aaclip_last_error()
+    assert lib.aaclip_anomaly_head(seg, 1, 0, f, 0, None, 2, 576, 768, 336, 0, None, None, f, f, need, None) == -1
+    assert b"extrema" in lib.aaclip_last_error()
+    assert lib.aaclip_anomaly_head(seg, 1, 0, f, 0, None, 2, 576, 768, 336, 0, None, f, None, f, need, None) == -1
+    assert b"det" in lib.aaclip_last_error()
+
+
+def test_effective_levels_follow_the_reference_membership_test():
+    """model/adapter.py:100 taps block i when `i + 1 in self.levels`: duplicates fire once, order does not matter and
+    out-of-range levels never fire ([6, 6, 12] used to be rejected by aaclip_create)."""
+    from aaclip_b200.adapter import effective_levels
+    assert effective_levels([6, 12, 18, 24], 24) == [6, 12, 18, 24]
+    assert effective_levels([12, 6, 6, 24, 18, 12], 24) == [6, 12, 18, 24]
+    assert effective_levels([0, 6, 25, 24, -3], 24) == [6, 24]
+    assert effective_levels([30], 24) == []

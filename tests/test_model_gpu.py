@@ -319,8 +319,9 @@ def test_head_stream_shapes_vs_oracle(dtype, B, G, S, levels):
 
 
 def test_head_misaligned_and_unsupported_inputs_take_the_general_path():
-    """Level pointers that are not 16-byte aligned (a view into a larger buffer) and embed dims other than 768 cannot
-    use cp.async.bulk / the fixed-width kernel: the general kernels must serve them with the same results."""
+    """Embed dims other than 768 cannot use the fixed-width streaming kernel: the general kernels serve them with the
+    same results.  Level tensors that are not 16-byte aligned (a view into a larger buffer) are re-packed by the
+    Python front end; the C entry refuses them with a message instead of faulting."""
     import aaclip_oracle as orc
     from aaclip_b200 import ops
     gen = torch.Generator().manual_seed(9)
@@ -336,9 +337,18 @@ def test_head_misaligned_and_unsupported_inputs_take_the_general_path():
     big = torch.zeros(f768.numel() + 8, dtype=torch.bfloat16, device="cuda")
     view = big[1:1 + f768.numel()].view_as(f768)   # 2-byte offset: 16-byte alignment lost
     view.copy_(f768)
+    assert view.data_ptr() % 16 != 0
     a, _ = ops.anomaly_head([view], T768.cuda(), S, ops.HEAD_TEST_MEDICAL)
     b, _ = ops.anomaly_head([f768.cuda()], T768.cuda(), S, ops.HEAD_TEST_MEDICAL)
-    assert (a - b).abs().max().item() < HEAD_TOL
+    assert torch.equal(a, b)
+    import ctypes as C
+    from aaclip_b200 import _lib
+    lib = _lib.load()
+    arr = (C.c_void_p * 1)(view.data_ptr())
+    ws = torch.empty(lib.aaclip_anomaly_head_workspace_bytes(1, B, G * G), dtype=torch.uint8, device="cuda")
+    rc = lib.aaclip_anomaly_head(arr, 1, 1, T768.cuda().data_ptr(), 0, None, B, G * G, 768, S, 1, a.data_ptr(), None, None,
+                                 ws.data_ptr(), ws.numel(), None)
+    assert rc == -1 and b"aligned" in lib.aaclip_last_error()
 
 
 def test_head_linearity_and_constant_property():
