@@ -35,6 +35,15 @@ class _Block(nn.Module):
             ("c_proj", nn.Linear(mlp_width, d_model)),
         ]))
 
+    def forward(self, x, attn_mask=None):
+        """The reference block returns (x, head-averaged attention weights) and is called per layer by AdaptedCLIP.forward
+        (model/transformer.py:239-258, model/adapter.py:91).  Here the per-layer loop lives inside the engine (the
+        [L, L] attention matrix is never materialised: flash-style kernel), so a block of this container cannot be
+        called on its own - pass the reference's own CLIP to AdaptedCLIP if module-level calls are needed elsewhere."""
+        raise NotImplementedError(
+            "aaclip_b200.clip._Block holds parameters only: the block arithmetic runs inside the CUDA engine through "
+            "AdaptedCLIP.forward / encode_text (no per-block entry, no attention-weight output)")
+
 
 class _Transformer(nn.Module):
     def __init__(self, width: int, layers: int, heads: int, mlp_width: int, quick_gelu: bool):
@@ -141,3 +150,61 @@ def load_checkpoint(model: CLIP, state_dict, strict: bool = True):
     if not strict:
         sd = {k: v for k, v in sd.items() if k in own}
     return model.load_state_dict(sd, strict=strict)
+
+
+# ---------------------------------------------------------------------------------------------- OpenAI checkpoints
+def _unwrap_openai(state_dict) -> dict:
+    """model/openai.py:58-72: a checkpoint is either the JIT archive's state dict itself or {"state_dict": {"module.x": ...}}."""
+    sd = state_dict
+    if isinstance(sd, dict) and "state_dict" in sd and "visual.conv1.weight" not in sd:
+        sd = {k[7:] if k.startswith("module.") else k: v for k, v in sd["state_dict"].items()}
+    return dict(sd)
+
+
+def cfg_from_openai_state_dict(state_dict, img_size: Optional[int] = None, quick_gelu: bool = False) -> ModelCfg:
+    """Architecture of an OpenAI CLIP ViT state dict from its tensor shapes, as model/model.py:317-343 infers it
+    (vision width / layers / patch size / grid from conv1, the in_proj weights and the positional embedding; text
+    width, heads = width // 64, layers, context, vocabulary).  `img_size` overrides the checkpoint's resolution (the
+    reference builds CLIP(**json, image_size=img_size) and resamples the positional embedding: model/clip.py:112-131);
+    `quick_gelu` stays False as in the shipped ViT-L-14-336.json (the model the reference actually runs uses nn.GELU,
+    model/model.py:84, whatever activation the checkpoint was trained with)."""
+    sd = _unwrap_openai(state_dict)
+    if "visual.proj" not in sd:
+        raise ValueError("not a ViT CLIP state dict (visual.proj missing): ResNet towers are outside the hot path")
+    width = sd["visual.conv1.weight"].shape[0]
+    layers = len([k for k in sd if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
+    patch = sd["visual.conv1.weight"].shape[-1]
+    grid = round((sd["visual.positional_embedding"].shape[0] - 1) ** 0.5)
+    if grid * grid + 1 != sd["visual.positional_embedding"].shape[0]:
+        raise ValueError("visual.positional_embedding is not 1 + a square grid")
+    mlp = sd["visual.transformer.resblocks.0.mlp.c_fc.weight"].shape[0]
+    t_width = sd["ln_final.weight"].shape[0]
+    t_layers = len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks")})
+    return ModelCfg(image_size=int(img_size) if img_size else patch * grid, patch_size=patch, width=width, layers=layers,
+                    heads=max(1, width // 64), mlp_ratio=mlp / width, embed_dim=sd["text_projection"].shape[1],
+                    quick_gelu=quick_gelu, t_context=sd["positional_embedding"].shape[0],
+                    t_vocab=sd["token_embedding.weight"].shape[0], t_width=t_width, t_heads=max(1, t_width // 64),
+                    t_layers=t_layers)
+
+
+def load_openai_state_dict(state_dict, img_size: Optional[int] = None, quick_gelu: bool = False) -> CLIP:
+    """An OpenAI CLIP ViT checkpoint (the JIT archive's state dict: fp16 Linear / Conv / attention / projection
+    tensors, fp32 LayerNorm and embeddings, plus the three metadata scalars) -> a loaded `CLIP` container, the way the
+    reference's create_model(pretrained="openai") gets there:
+
+        load_openai_model -> build_model_from_openai_state_dict -> .float()      model/openai.py:66-77, model/model.py:311-368
+        state_dict = model_pre.state_dict(); CLIP(**json, image_size=img_size)   model/clip.py:112-126
+        resize_pos_embed(state_dict, model); load_state_dict(strict=True)        model/clip.py:130-131, model/model.py:395-426
+
+    i.e. metadata keys dropped, every tensor widened to fp32 (exact), the positional embedding resampled (bicubic,
+    antialias, align_corners=False) when `img_size` differs from the checkpoint's, strict load.  Wrap the result in
+    AdaptedCLIP: the engine packs GEMM operands to bf16 from these fp32 values."""
+    sd = _unwrap_openai(state_dict)
+    cfg = cfg_from_openai_state_dict(sd, img_size, quick_gelu)
+    for k in ("input_resolution", "context_length", "vocab_size"):   # model/model.py:362-363
+        sd.pop(k, None)
+    sd = {k: (v.float() if torch.is_floating_point(v) else v) for k, v in sd.items()}
+    model = CLIP(cfg, text=True)
+    resize_pos_embed(sd, model.visual.grid_size[0])
+    model.load_state_dict(sd, strict=True)
+    return model.eval()

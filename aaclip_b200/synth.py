@@ -182,3 +182,24 @@ def head_inputs(batch: int, grid: int, embed_dim: int = 768, levels: int = 4, se
     tb = norm(torch.randn(batch, embed_dim, 2, generator=g), dim=1)
     det = norm(torch.randn(batch, embed_dim, generator=g), dim=-1) * 0.3
     return feats, tb, det
+
+
+def openai_style_state_dict(cfg: ModelCfg, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """clip_state_dict(cfg, seed) in the shape of an OpenAI JIT archive's state dict: the tensors
+    convert_weights_to_lp touches (Linear / Conv weights and biases, the attention in_proj tensors, `proj`,
+    `text_projection`: model/model.py:265-286) in fp16, LayerNorm and embeddings in fp32, plus the three metadata
+    scalars that build_model_from_openai_state_dict drops (model/model.py:362-363).  For the checkpoint-ingestion tests."""
+    sd = dict(clip_state_dict(cfg, seed))
+    lp = ("conv1.weight", "in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias", "c_fc.weight", "c_fc.bias",
+          "c_proj.weight", "c_proj.bias")
+    for k in list(sd):
+        if k.endswith(lp) or k in ("visual.proj", "text_projection"):
+            sd[k] = sd[k].half()
+    sd["input_resolution"] = torch.tensor(cfg.image_size)
+    sd["context_length"] = torch.tensor(cfg.t_context)
+    sd["vocab_size"] = torch.tensor(cfg.t_vocab)
+    return sd
+
+
+OPENAI_TINY = dict(image_size=56, patch_size=14, width=128, layers=2, heads=2, embed_dim=32, t_context=77, t_vocab=128,
+                   t_width=64, t_heads=1, t_layers=2)

@@ -1,14 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the AA-CLIP inference hot path on B200 (BASELINE.json: anomaly maps/s, 336 px, ViT-L/14).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch-per-gpu 64] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch-per-gpu B] [--impl b200|reference]
+                    [--sweep] [--text] [--no-cpu-baseline] [--no-e2e] [--no-gpu-baseline] [--no-drop-in]
 
 A step = one pass of the hot path over one batch of synthetic images: ViT-L/14-336 visual encoder with the 6
 residual adapters, 4 taps -> ln_post -> seg/det projections -> L2 normalise -> anchor similarity -> gaussian
 blur + bilinear upsample -> level-summed 336x336 anomaly maps and image scores (test.py:80-93), through
-aaclip_forward_fused (device-resident inputs: `value`) and aaclip_forward_fused_host (pinned host buffers,
+aaclip_forward_fused (device-resident inputs: `value`) and aaclip_submit_host / aaclip_wait_host (pinned host buffers,
 H2D + D2H inside the timed region: `e2e`).  N > 1: one process per GPU (torchrun), batch sharded data-parallel,
-one NCCL all-gather of the image scores per step, max-over-ranks timing.
+one NCCL all-gather of the image scores per step, max-over-ranks timing.  Per-GPU batch: 64 (BASELINE.json
+configs[1]); at N = 8 the default is 128 per GPU = global batch 1024 (configs[2]).
+
+Extra legs on rank 0 at N = 1 (all reported inside the one JSON line):
+  roofline / roofline_head   per-kernel-class CUDA events of the same step; the head (aaclip_anomaly_head) timed as a
+                             replayed CUDA graph of back-to-back calls, bf16 and fp32 tokens
+  drop_in                    the reference's call sequence on the drop-in classes: model(image) + 4 x
+                             calculate_similarity_map + cat + sum (test.py:80-93), fp32 and bf16 tokens
+  torch_gpu_baseline         the oracle (stock PyTorch ops, what the reference runs) on the same B200: fp32 with TF32
+                             off / on, and bf16 autocast - the like-for-like GPU baseline of SURVEY 8(d)
+  cpu_baseline               the oracle on the host cores: 4 threads (the reference's pin, test.py:28-35) and all
+                             cores, batch 1 and batch 8
+  --sweep                    BASELINE.json configs[4]: batch 1 .. 2048 with the roofline fractions
+  --text                     BASELINE.json configs[3]: text-anchor path + similarity against cached patch features
 
 --impl reference times the CPU restatement of the reference path (oracle/aaclip_oracle.py, kind "port": the
 Python reference itself cannot travel to the GPU box) on the host cores, on a bounded sample of the workload.
@@ -16,6 +30,7 @@ Python reference itself cannot travel to the GPU box) on the host cores, on a bo
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +43,7 @@ sys.path.insert(0, ROOT)
 
 F_IMG = 393_708_404_736          # algorithmic FLOP per image
 HEAD_BYTES_IMG = 3_993_604       # fused head algorithmic bytes per image, bf16 tokens
+HEAD_BYTES_IMG_F32 = 7_532_548   # fp32 tokens
 METRIC = "anomaly maps/sec (336px, ViT-L-14)"
 UNIT = "images/s"
 
@@ -37,12 +53,15 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--batch-per-gpu", type=int, default=0, help="images per GPU and step (0: 64, or 128 at --gpus 8)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cta-group", type=int, default=0)
-    ap.add_argument("--cpu-baseline-images", type=int, default=-1, help="images the CPU baseline leg runs (-1 auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-drop-in", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="append the batch sweep 1..2048 (BASELINE.json configs[4])")
+    ap.add_argument("--text", action="store_true", help="append the text-anchor path (BASELINE.json configs[3])")
     return ap.parse_args()
 
 
@@ -53,6 +72,31 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def kernel_source_sha() -> str:
+    """sha256 over the kernel sources: ties a committed ncu capture to the code it was taken on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "aaclip_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernels from the ncu --set full capture committed for THIS kernel source
+    (profiles/r2_ncu_traffic.json, written by tools/ncu_traffic.py); None when there is none or it is stale."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, "no ncu capture committed (profiles/r2_ncu_traffic.json)"
+    d = json.load(open(p))
+    sha = kernel_source_sha()
+    if d.get("kernel_source_sha") != sha:
+        return None, (f"stale: capture taken on kernel sources {d.get('kernel_source_sha')} (commit {d.get('commit')}), "
+                      f"this tree is {sha}")
+    return d, f"ncu --set full, commit {d.get('commit')}, kernel sources {sha}"
 
 
 class ClockSampler:
@@ -141,30 +185,120 @@ class ClockSampler:
                 "source": self.source}
 
 
-def cpu_port_images_per_s(n_images: int, threads: int):
-    """Times the oracle (CPU restatement of the reference path) on `n_images` synthetic images, batch 1 each
-    (BASELINE.json configs[0]), after one warm-up image.  Returns (images/s, seconds)."""
-    import torch
+# ----------------------------------------------------------------------------------------------- baselines (oracle)
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import aaclip_oracle as orc
+    return orc
+
+
+_CPU_WEIGHTS = None
+
+
+def cpu_port_rate(batch: int, n_batches: int, threads: int):
+    """The oracle (CPU restatement of the reference path, test.py:80-93) on `n_batches` synthetic batches of `batch`
+    images with `threads` torch threads, after one warm-up batch.  Returns (images/s, seconds)."""
+    global _CPU_WEIGHTS
+    import torch
+    orc = _oracle()
     from aaclip_b200 import synth
     torch.set_num_threads(threads)
     cfg = synth.VIT_L_14_336
-    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    if _CPU_WEIGHTS is None:
+        _CPU_WEIGHTS = (synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0))
+    sd, ia = _CPU_WEIGHTS
     T = synth.anchors(cfg, 1)
-    imgs = synth.images(n_images + 1, cfg, seed=1)
+    imgs = synth.images(batch * 2, cfg, seed=1)
 
     def one(i):
         with torch.no_grad():
-            seg, det = orc.visual_forward(sd, ia, imgs[i:i + 1])
+            x = imgs[(i % 2) * batch:(i % 2 + 1) * batch]
+            seg, det = orc.visual_forward(sd, ia, x)
             return orc.predict(seg, det, T, cfg.image_size, "Industrial")
 
     one(0)
     t0 = time.perf_counter()
-    for i in range(1, n_images + 1):
-        one(i)
+    for i in range(n_batches):
+        one(i + 1)
     dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return batch * n_batches / dt, dt
+
+
+def cpu_baselines():
+    """4 threads (the reference pins 4, test.py:28-35) and all cores, batch 1 (configs[0]) and 8."""
+    cores = os.cpu_count() or 1
+    legs = {}
+    for name, threads, batch, n in (("all_cores_b1", cores, 1, 12), ("all_cores_b8", cores, 8, 2),
+                                    ("threads4_b1", 4, 1, 4), ("threads4_b8", 4, 8, 1)):
+        v, secs = cpu_port_rate(batch, n, threads)
+        legs[name] = {"value": v, "unit": UNIT, "threads": threads, "batch": batch, "images": batch * n, "seconds": secs}
+    head = legs["all_cores_b1"]
+    return {"value": head["value"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{head['images']} images, batch 1 each (BASELINE.json configs[0]), {head['seconds']:.1f} s, torch fp32 "
+                      "restatement of the reference path (oracle/aaclip_oracle.py) on all host cores",
+            "legs": legs,
+            "note": "a CPU port on host cores is context, not the comparable baseline: see torch_gpu_baseline for the "
+                    "reference's own op sequence on this GPU"}
+
+
+def torch_gpu_baseline(B: int, inputs, anchors, eng_maps, eng_scores):
+    """the reference's op sequence (stock PyTorch / ATen / cuBLAS / cuDNN kernels, as the reference's
+    model(image) + calculate_similarity_map x4 would launch them) on this B200, same weights and inputs, CUDA events.
+    The oracle is the checker's restatement of that sequence; it is the baseline here, never the product."""
+    import torch
+    orc = _oracle()
+    from aaclip_b200 import synth
+    cfg = synth.VIT_L_14_336
+    sd = {k: v.cuda() for k, v in synth.clip_state_dict(cfg, 0, text=False).items()}
+    ia = {k: v.cuda() for k, v in synth.image_adapter_state_dict(cfg, 0).items()}
+    out = {"batch": B, "what": "oracle.visual_forward + oracle.predict (model/adapter.py:67-112 + test.py:83-93) on cuda, "
+                               "stock PyTorch kernels"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def run(x):
+        with torch.no_grad():
+            seg, det = orc.visual_forward(sd, ia, x)
+            return orc.predict(seg, det, anchors, cfg.image_size, "Industrial")
+
+    def timed(fn, reps):
+        fn(inputs[0])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            r = fn(inputs[i % len(inputs)])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    try:
+        for name, tf32, reps in (("fp32_tf32_off", False, 2), ("fp32_tf32_on", True, 3)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            ms, (m, s) = timed(run, reps)
+            out[name] = {"ms_per_step": ms, "images_per_s": B / (ms / 1e3), "allow_tf32": tf32}
+            if name == "fp32_tf32_off" and eng_maps is not None:   # parity of the product against it, same run
+                mm = lambda x: (x - x.min()) / (x.max() - x.min())
+                ref_m, ref_s = run(inputs[0])
+                out["parity_vs_engine"] = {
+                    "normalised_map_max_abs": float((mm(eng_maps) - mm(ref_m)).abs().max()),
+                    "raw_map_max_abs": float((eng_maps - ref_m).abs().max()),
+                    "score_max_abs": float((eng_scores - ref_s).abs().max()),
+                    "ranking_identical": bool(torch.equal(eng_scores.argsort(), ref_s.argsort())),
+                    "tolerance": "normalised map <= 1e-2 (north star), identical ranking"}
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+
+        def run_bf16(x):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return run(x)
+        ms, _ = timed(run_bf16, 5)
+        out["bf16_autocast"] = {"ms_per_step": ms, "images_per_s": B / (ms / 1e3)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del sd, ia
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args, out):
@@ -173,10 +307,8 @@ def run_reference(args, out):
         return
     threads = os.cpu_count() or 1
     per_step = 2  # bounded sample of the batch-64 step
-    total = per_step * (args.steps + args.warmup)
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import aaclip_oracle as orc
+    orc = _oracle()
     from aaclip_b200 import synth
     torch.set_num_threads(threads)
     cfg = synth.VIT_L_14_336
@@ -205,7 +337,8 @@ def run_reference(args, out):
                    "sample": f"{per_step} images per step of the batch-64 step", "device": "host CPU"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step}-image steps x {args.steps}, torch fp32 restatement of the reference path "
-                                   "(oracle/aaclip_oracle.py); the Python reference itself cannot travel to the GPU box"},
+                                   "(oracle/aaclip_oracle.py) on all host cores; a CPU port, not a like-for-like baseline "
+                                   "(the Python reference itself cannot travel to the GPU box)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,6 +352,196 @@ def _claim_stdout():
     saved = os.dup(1)
     os.dup2(2, 1)
     return os.fdopen(saved, "w")
+
+
+# ----------------------------------------------------------------------------------------------- extra legs
+def graph_time(fn, n):
+    """Device time per call of fn(i): n calls captured into ONE CUDA graph, replayed twice under CUDA events - no
+    Python / launch overhead between the kernels (the entries allocate nothing and never synchronise)."""
+    import torch
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(n):
+                fn(i)
+        g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        g.replay()
+        e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (2 * n)
+
+
+def head_roofline(B, cfg, anchors, peaks):
+    """HBM roofline of aaclip_anomaly_head (the A7 contract: n levels of normalised tokens + det in, map + score +
+    extrema out): head_stream_kernel + maps_from_dots_kernel, the kernels calculate_similarity_map /
+    similarity_maps_summed run.  Inputs alternate between sets larger than the 126 MB L2."""
+    import torch
+    from aaclip_b200 import ops
+
+    def rate(hb, dtype, nl):
+        es = 2 if dtype == torch.bfloat16 else 4
+        copies = max(2, (300 << 20) // (hb * nl * cfg.patches * cfg.embed_dim * es) + 1)
+        sets = [[torch.nn.functional.normalize(torch.randn(hb, cfg.patches, cfg.embed_dim, device="cuda"), dim=-1).to(dtype)
+                 for _ in range(nl)] for _ in range(copies)]
+        det = torch.randn(hb, cfg.embed_dim, device="cuda")
+        ms = graph_time(lambda i: ops.anomaly_head(sets[i % copies], anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL,
+                                                   det=det, want_extrema=True), 12)
+        byts = hb * (nl * cfg.patches * cfg.embed_dim * es + cfg.image_size ** 2 * 4 + cfg.embed_dim * 4 + 4 + 8)
+        return {"batch": hb, "ms": ms, "achieved": byts / (ms / 1e3) / 1e9, "frac": byts / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                "images_per_s": hb / (ms / 1e3), "bytes_per_image": byts // hb, "input_sets": copies}
+
+    main = rate(B, torch.bfloat16, 4)
+    head = {"bound": "hbm",
+            "kernel": "aaclip_anomaly_head = head_stream_kernel (cp.async.bulk-staged token stream -> one scalar per patch) + "
+                      "maps_from_dots_kernel (blur, upsample, map rows, extrema), chained by programmatic dependent launch; "
+                      "the kernels calculate_similarity_map / similarity_maps_summed run",
+            "achieved": main["achieved"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": main["frac"], "ms": main["ms"],
+            "images_per_s": main["images_per_s"], "bytes_per_image": main["bytes_per_image"],
+            "how": "12 back-to-back calls captured into one CUDA graph, replayed twice under CUDA events; inputs alternate "
+                   f"between {main['input_sets']} sets of 4 levels (> 126 MB L2 each pair): every call streams from HBM",
+            "tokens_f32": rate(B, torch.float32, 4),
+            "one_level_call_bf16": rate(B, torch.bfloat16, 1),
+            "at_4x_batch": rate(4 * B, torch.bfloat16, 4)}
+    return head
+
+
+def drop_in_leg(B, cfg, inputs, anchors, steps):
+    """The reference's own call sequence (test.py:80-93) on the drop-in classes: model(image) -> 4 levels of tokens + det,
+    4 x calculate_similarity_map, cat, sum, image score - with the reference's fp32 tokens and with bf16 tokens, and the
+    one-call form similarity_maps_summed.  CUDA events, device-resident inputs."""
+    import torch
+    from aaclip_b200 import synth
+    from aaclip_b200.adapter import AdaptedCLIP
+    from aaclip_b200.clip import CLIP
+    from aaclip_b200.forward_utils import calculate_similarity_map, similarity_maps_summed
+    clip = CLIP(cfg, text=False)
+    clip.load_state_dict(synth.clip_state_dict(cfg, 0, text=False), strict=False)
+    out = {"batch": B, "what": "AdaptedCLIP.forward + calculate_similarity_map x4 + cat + sum + score (test.py:80-93)"}
+    for name, dt in (("tokens_f32", torch.float32), ("tokens_bf16", torch.bfloat16)):
+        model = AdaptedCLIP(clip_model=clip, image_adapt_until=cfg.image_adapt_until, levels=list(cfg.levels), relu=False,
+                            max_batch=B, seg_dtype=dt).to("cuda").eval()
+        model.image_adapter.load_state_dict(synth.image_adapter_state_dict(cfg, 0))
+
+        def ref_style(x):
+            feats, det = model(x)
+            score = ((det @ anchors)[:, 1] + 1) / 2
+            maps = torch.cat([calculate_similarity_map(f, anchors, cfg.image_size, test=True, domain="Industrial")
+                              for f in feats], dim=1).sum(1)
+            return maps, score
+
+        def one_call(x):
+            feats, det = model(x)
+            return similarity_maps_summed(feats, anchors, cfg.image_size, "Industrial", det_feature=det)
+
+        leg = {}
+        for lname, fn in (("per_level_calls", ref_style), ("summed_call", one_call)):
+            for i in range(2):
+                fn(inputs[i % len(inputs)])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                fn(inputs[i % len(inputs)])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            leg[lname] = {"ms_per_step": ms, "images_per_s": B / (ms / 1e3)}
+        out[name] = leg
+        model._engine.close()
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
+def sweep_leg(cfg, anchors, peaks, max_b=2048):
+    """BASELINE.json configs[4]: batch 1 .. 2048 (chunks of <= 256 images), all four taps, fused head."""
+    import torch
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    eng = Engine(cfg, device=torch.cuda.current_device(), max_batch=256, text=False)
+    eng.load_state_dicts(synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0), None)
+    rows = []
+    side = torch.cuda.Stream()
+    B = 1
+    while B <= max_b:
+        g = torch.Generator(device="cuda").manual_seed(B)
+        img = torch.randn(B, 3, cfg.image_size, cfg.image_size, device="cuda", generator=g)
+        outs = (torch.empty(B, cfg.image_size, cfg.image_size, device="cuda"), torch.empty(B, device="cuda"))
+        reps = max(2, min(20, 2048 // B))
+        with torch.cuda.stream(side):
+            for _ in range(3):   # first sight eager, second captured, third replayed (stable pointers)
+                eng.forward_fused(img, anchors, out=outs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                eng.forward_fused(img, anchors, out=outs)
+            e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = F_IMG * B / (ms / 1e3) / 1e12
+        rows.append({"batch": B, "ms": ms, "images_per_s": B / (ms / 1e3), "tflops": tf,
+                     "frac_of_burst_peak": tf / peaks["bf16_tflops"], "frac_of_sustained_peak": tf / peaks["bf16_tflops_sustained"]})
+        del img, outs
+        B *= 2
+    eng.close()
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE.json configs[4]: batch sweep with taps at layers 6/12/18/24, fused forward, CUDA graphs",
+            "rows": rows}
+
+
+def text_leg(cfg, peaks):
+    """BASELINE.json configs[3]: text encoder with text adapter over the prompt templates x 15 class names (240 sentences,
+    dataset/constants.py:135-147; synthetic token ids), anchors [768,2] per class, then similarity against cached patch
+    features (64 images x 4 levels) for every class."""
+    import torch
+    from aaclip_b200 import ops, synth
+    from aaclip_b200._lib import check, cur_stream, ptr
+    from aaclip_b200.engine import Engine
+    eng = Engine(cfg, device=torch.cuda.current_device(), max_batch=1, max_text=256, text=True)
+    eng.load_state_dicts(synth.clip_state_dict(cfg, 0), synth.image_adapter_state_dict(cfg, 0), synth.text_adapter_state_dict(cfg, 0))
+    n_cls, n_norm, n_abn = 15, 7, 9
+    tok = synth.tokens(n_cls * (n_norm + n_abn), cfg, seed=2).cuda()
+    out_a = torch.empty(n_cls, cfg.embed_dim, 2, device="cuda")
+
+    def anchors_all():
+        emb = eng.text_forward(tok)   # one batched pass over all 240 sentences
+        for c in range(n_cls):
+            base = c * (n_norm + n_abn)
+            check(eng.lib.aaclip_text_anchor(ptr(emb[base:base + n_norm]), n_norm, cfg.t_width, ptr(out_a[c]), 0, cur_stream(emb.device)))
+            check(eng.lib.aaclip_text_anchor(ptr(emb[base + n_norm:base + n_norm + n_abn]), n_abn, cfg.t_width, ptr(out_a[c]), 1,
+                                             cur_stream(emb.device)))
+        return out_a
+
+    def ev(fn, reps):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = ev(anchors_all, 5)
+    A = anchors_all()
+    feats = [torch.nn.functional.normalize(torch.randn(64, cfg.patches, cfg.embed_dim, device="cuda"), dim=-1).bfloat16() for _ in range(4)]
+    ms2 = ev(lambda: [ops.anomaly_head(feats, A[c], cfg.image_size, ops.HEAD_TEST_INDUSTRIAL) for c in range(n_cls)], 5)
+    flop = 240 * 13.6e9
+    eng.close()
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE.json configs[3]: 240 prompt sentences x 77 tokens through the 12-layer text tower with the "
+                        "text adapter -> 15 class anchors [768,2]; then 64 cached images x 4 levels against every class",
+            "text_anchors_ms": ms, "sentences_per_s": 240 / (ms / 1e3), "text_tflops": flop / (ms / 1e3) / 1e12,
+            "similarity_ms_15_classes": ms2, "maps_per_s": 64 * n_cls / (ms2 / 1e3),
+            "similarity_hbm_frac": 64 * n_cls * HEAD_BYTES_IMG / (ms2 / 1e3) / 1e9 / peaks["hbm_gbs"]}
 
 
 def main():
@@ -246,14 +569,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cfg = synth.VIT_L_14_336
-    B = args.batch_per_gpu
+    # BASELINE.json configs[1]: 64 images on one B200; configs[2]: 8 x B200, global batch 1024 = 128 per GPU
+    B = args.batch_per_gpu if args.batch_per_gpu > 0 else (128 if world == 8 else 64)
     total = B * world
     b0, b1 = shard_range(total, rank, world)
     assert b1 - b0 == B
     peaks = load_peaks()
 
-    # the clock sampler (a child nvidia-smi) starts before the weights are uploaded: its NVML start-up, which can stall
-    # the driver for ~100 ms, must not land in the timed region
+    # the clock sampler starts before the weights are uploaded: its NVML start-up, which can stall the driver for
+    # ~100 ms, must not land in the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -264,17 +588,18 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     inputs = [torch.randn(B, 3, cfg.image_size, cfg.image_size, device="cuda", generator=g) for _ in range(n_rot)]
 
-    # caller-owned outputs, one pair per rotating input: with stable pointers on a non-default stream the engine
+    # caller-owned outputs, one set per rotating input: with stable pointers on a non-default stream the engine
     # replays each step as one CUDA graph launch (captured the second time a (batch, pointers) key occurs)
     outs = [(torch.empty(B, cfg.image_size, cfg.image_size, device="cuda"), torch.empty(B, device="cuda"))
             for _ in range(n_rot)]
+    gathered = torch.empty(total, device="cuda") if world > 1 else None   # one collective straight into this buffer
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
 
     def step(i):
         maps, scores = eng.forward_fused(inputs[i % n_rot], anchors, "Industrial", out=outs[i % n_rot])
         if world > 1:
-            scores = gather_scores(scores, total)
+            scores = gather_scores(scores, total, out=gathered)
         return maps, scores
 
     def sync_all():
@@ -333,6 +658,7 @@ def main():
     attn_flop_img = 24 * 2 * 2 * 16 * 577 * 577 * 64
     gemm_flop_step = (F_IMG - attn_flop_img) * B
     gemm_tflops = gemm_flop_step / (gemm_ms / 1e3) / 1e12
+    traffic, traffic_note = load_traffic()
     roofline = {
         "bound": "tensor", "kernel": "gemm::gemm_kernel (tcgen05, all encoder/adapter/projection GEMMs)",
         "achieved": gemm_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -340,16 +666,15 @@ def main():
         "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json); burst {peaks['bf16_tflops']}",
         "flop_per_launch_avg": gemm_flop_step / max(gemm_launches, 1), "launches_per_step": gemm_launches,
         "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_step": gemm_ms / tot_ms,
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures of the two
-        # largest GEMMs (profiles/r1_ncu_full_summaries.txt, r1c_gemm_full): c_fc with folded ln_2 336 MB (algorithmic
-        # 386 MB: part of the 302 MB bf16 output is still in L2 when the kernel ends), c_proj with the residual +
-        # bf16-copy + statistics epilogue 703 MB (algorithmic 692 MB: h 302, W 8, x read 151 + write 151, bf16 copy 76,
-        # partial sums 2)
-        "traffic": (336.4e6 + 702.6e6) / 2, "traffic_detail": {"gemm_fc": 336.4e6, "gemm_proj": 702.6e6,
-                                                                "algorithmic": {"gemm_fc": 386.4e6, "gemm_proj": 691.5e6}},
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the captured launches of the two largest
+        # GEMM classes (c_fc and c_proj); only when the capture was taken on exactly these kernel sources
+        "traffic": (None if traffic is None or B != traffic.get("batch") else traffic.get("gemm_traffic_avg_bytes")),
+        "traffic_source": traffic_note,
+        "traffic_detail": None if traffic is None else traffic.get("kernels"),
         "achieved_in_timed_region_estimate": gemm_tflops * (span_ms / (ms / args.steps)),
         "whole_step_tflops": F_IMG * B / (ms / args.steps / 1e3) / 1e12,
         "whole_step_frac": F_IMG * B / (ms / args.steps / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
+        "whole_step_frac_of_burst_peak": F_IMG * B / (ms / args.steps / 1e3) / 1e12 / peaks["bf16_tflops"],
     }
     if "attention" in kern:
         kern["attention"]["tflops"] = attn_flop_img * B / (kern["attention"]["ms_per_step"] / 1e3) / 1e12
@@ -361,22 +686,23 @@ def main():
         h_img = [inputs[i].cpu().pin_memory() for i in range(2)]
         h_maps = [torch.empty(B, S, S).pin_memory() for _ in range(2)]
         h_scores = [torch.empty(B).pin_memory() for _ in range(2)]
+        h_ext = [torch.empty(B, 2).pin_memory() for _ in range(2)]
         h_anchor = anchors.cpu()
 
         def e2e_loop(n):
             # the loop of test.py:get_predictions over n batches through the pipelined host-buffer entry: every
-            # batch's H2D (images) and D2H (maps + scores) is inside; copies of neighbouring batches overlap compute
+            # batch's H2D (images) and D2H (maps + scores + extrema) is inside; copies of neighbouring batches overlap compute
             prev = None
             for i in range(n):
-                t = eng.submit_host(h_img[i % 2], h_anchor, h_maps[i % 2], h_scores[i % 2])
+                t = eng.submit_host(h_img[i % 2], h_anchor, h_maps[i % 2], h_scores[i % 2], extrema_out=h_ext[i % 2])
                 if prev is not None:
                     eng.wait_host(prev)
                     if world > 1:
-                        gather_scores(h_scores[(i - 1) % 2].cuda(non_blocking=True), total)
+                        gather_scores(h_scores[(i - 1) % 2].cuda(non_blocking=True), total, out=gathered)
                 prev = t
             eng.wait_host(prev)
             if world > 1:
-                gather_scores(h_scores[(n - 1) % 2].cuda(non_blocking=True), total)
+                gather_scores(h_scores[(n - 1) % 2].cuda(non_blocking=True), total, out=gathered)
 
         e2e_loop(3)
         sync_all()
@@ -393,9 +719,9 @@ def main():
         sync_ms = (time.perf_counter() - t1) / 3 * 1e3
         e2e = {"value": total * args.steps / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h_img[0].numel() * 4 + h_anchor.numel() * 4),
-               "d2h_bytes_per_step": int(h_maps[0].numel() * 4 + h_scores[0].numel() * 4),
+               "d2h_bytes_per_step": int(h_maps[0].numel() * 4 + h_scores[0].numel() * 4 + h_ext[0].numel() * 4),
                "api": "aaclip_submit_host / aaclip_wait_host (C ABI, pinned host buffers, two batches in flight: "
-                      "Engine.predict_stream)",
+                      "Engine.predict_stream); maps, scores and per-image map extrema come back",
                "synchronous_call_ms": sync_ms, "synchronous_call_images_per_s": B / (sync_ms / 1e3)}
 
         # the same loop fed RAW uint8 images (MVTec's 1024 x 1024 RGB): H2D of the bytes, then the loader's
@@ -425,89 +751,64 @@ def main():
                                   "h2d_bytes_per_step": int(h_raw[0].numel() + h_anchor.numel() * 4),
                                   "api": "aaclip_submit_host_u8: raw RGB bytes in, transform_x on the device "
                                          "(bit-exact with PIL + torchvision), fused forward, maps + scores out"}
-            from aaclip_b200 import ops as _ops
-            d_raw = h_raw[0].cuda()
-            for _ in range(3):
-                _ops.preprocess_u8(d_raw, S)
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            for _ in range(10):
-                _ops.preprocess_u8(d_raw, S)
-            p1.record()
-            torch.cuda.synchronize()
-            pms = p0.elapsed_time(p1) / 10
-            pbytes = B * (3 * R * R + 12 * S * S)
-            e2e["from_raw_u8"]["transform_x"] = {
-                "ms": pms, "images_per_s": B / (pms / 1e3), "algorithmic_GBps": pbytes / (pms / 1e3) / 1e9,
-                "frac_of_hbm": pbytes / (pms / 1e3) / 1e9 / peaks["hbm_gbs"],
-                "bound": "integer ALU (3 x 12-tap fixed-point MACs per output byte), not HBM"}
-            del d_raw, h_raw
+            del h_raw
         except Exception as e:  # never sink the headline line
             e2e["from_raw_u8"] = {"error": str(e)}
 
-    # ---- head kernel alone (HBM roofline of the fused anomaly-map head, A7 contract: 4 bf16 levels in, map out)
-    head = None
-    try:
-        from aaclip_b200 import ops
+    solo = rank == 0 and world == 1
+    legs = {}
 
-        def head_rate(hb):
-            # two rotating input sets of 4 levels: at hb = 64 one set is 226 MB, so every call streams from HBM
-            sets = [[torch.nn.functional.normalize(torch.randn(hb, cfg.patches, cfg.embed_dim, device="cuda"), dim=-1)
-                     .to(torch.bfloat16) for _ in range(4)] for _ in range(2)]
-            det = torch.randn(hb, cfg.embed_dim, device="cuda")
-            for i in range(3):
-                ops.anomaly_head(sets[i % 2], anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 20
-            h0.record()
-            for i in range(reps):
-                ops.anomaly_head(sets[i % 2], anchors, cfg.image_size, ops.HEAD_TEST_INDUSTRIAL, det=det)
-            h1.record()
-            torch.cuda.synchronize()
-            hms = h0.elapsed_time(h1) / reps
-            return hms, HEAD_BYTES_IMG * hb / (hms / 1e3) / 1e9
+    def leg(name, enabled, fn):
+        if not (solo and enabled):
+            return
+        try:
+            legs[name] = fn()
+        except Exception as e:   # an extra leg must never sink the headline line
+            legs[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
 
-        hms, gbs = head_rate(B)
-        hms4, gbs4 = head_rate(4 * B)
-        head = {"bound": "hbm", "kernel": "head_fused_kernel (aaclip_anomaly_head: cluster of 8 CTAs per image, dots -> DSMEM gather -> blur -> bilinear -> map + score)", "achieved": gbs,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "ms": hms,
-                "images_per_s": B / (hms / 1e3),
-                "note": "inputs alternate between two sets of 4 levels (2 x 226 MB at batch 64 > 126 MB L2): every call streams from HBM; "
-                        "at batch 64 the 64 clusters are a single wave, so the load phase and the blur / upsample / store phase do not overlap",
-                "at_4x_batch": {"batch": 4 * B, "ms": hms4, "achieved": gbs4, "frac": gbs4 / peaks["hbm_gbs"],
-                                "images_per_s": 4 * B / (hms4 / 1e3)}}
-    except Exception as e:  # the head microbench must never sink the headline line
-        head = {"error": str(e)}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n = args.cpu_baseline_images if args.cpu_baseline_images >= 0 else 48
-        threads = os.cpu_count() or 1
-        v, secs = cpu_port_images_per_s(n, threads)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{n} images, batch 1 each (BASELINE.json configs[0]), {secs:.1f} s, torch fp32 "
-                                  "restatement of the reference path (oracle/aaclip_oracle.py)"}
+    leg("roofline_head", True, lambda: head_roofline(B, cfg, anchors, peaks))
+    leg("drop_in", not args.no_drop_in, lambda: drop_in_leg(B, cfg, inputs, anchors, max(3, min(args.steps, 10))))
+    leg("torch_gpu_baseline", not args.no_gpu_baseline,
+        lambda: torch_gpu_baseline(B, inputs, anchors, *eng.forward_fused(inputs[0], anchors, "Industrial")))
+    leg("batch_sweep", args.sweep, lambda: sweep_leg(cfg, anchors, peaks))
+    leg("text_path", args.text, lambda: text_leg(cfg, peaks))
+    if solo and "torch_gpu_baseline" in legs and "error" not in legs["torch_gpu_baseline"]:
+        for k in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast"):
+            legs["torch_gpu_baseline"][k]["speedup_of_this_path"] = value / legs["torch_gpu_baseline"][k]["images_per_s"]
+    leg("cpu_baseline", not args.no_cpu_baseline, cpu_baselines)
 
     if rank == 0:
+        workload = ("single B200 bf16 batch 64: ViT-L-14-336 visual encoder + residual adapters + anomaly-map head producing "
+                    "336x336 pixel maps and image scores (BASELINE.json configs[1])")
+        if world > 1:
+            workload = (f"{world} x B200 data-parallel, global batch {total} ({B} per GPU) synthetic images, per-GPU shards, "
+                        "image-score gather over NVLink" + (" (BASELINE.json configs[2])" if total == 1024 and world == 8 else
+                                                            " (BASELINE.json configs[1] per GPU)"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "single B200 bf16 batch 64: ViT-L-14-336 visual encoder + residual adapters + "
-                                   "anomaly-map head producing 336x336 pixel maps and image scores (BASELINE.json configs[1])",
+            "config": {"workload": workload,
                        "batch_per_gpu": B, "global_batch": total, "image_size": cfg.image_size,
                        "parallelism": f"dp{world}", "weights": "random-init (synthetic, seed 0)",
                        "precision": "bf16 GEMM/attention operands, fp32 accumulation, residual stream, LayerNorm, softmax, head",
                        "l2": f"inputs rotate over {n_rot} batches ({n_rot * B * 3 * cfg.image_size ** 2 * 4 / 1e6:.0f} MB > 126 MB L2); "
                              "per-step activation traffic (>1.3 GB) exceeds L2",
                        "outputs_finite": finite},
-            "roofline": roofline, "roofline_head": head, "kernels": kern,
+            "roofline": roofline, "roofline_head": legs.get("roofline_head"), "kernels": kern,
             "profiled_step": {"span_ms": span_ms, "sum_kernel_ms": tot_ms, "idle_between_kernels_ms": span_ms - tot_ms,
-                              "note": "3 extra steps (after 3 discarded) with CUDA events around every launch"}, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                              "note": "3 extra steps (after 3 discarded) with CUDA events around every launch"},
+            "cpu_baseline": legs.get("cpu_baseline"), "torch_gpu_baseline": legs.get("torch_gpu_baseline"),
+            "drop_in": legs.get("drop_in"), "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms),
                         "all": [round(x, 3) for x in step_ms]},
         }
+        if "batch_sweep" in legs:
+            line["batch_sweep"] = legs["batch_sweep"]
+        if "text_path" in legs:
+            line["text_path"] = legs["text_path"]
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()

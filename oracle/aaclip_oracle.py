@@ -2,7 +2,8 @@
 
 A CPU, fp32, plain-PyTorch restatement of the reference (wei-paul/AA-CLIP) inference hot path, written
 against state dicts so that it runs where /root/reference does not exist (the GPU box).  Only tests/,
-__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module; the
+__graft_entry__.smoke() and bench.py's baseline legs (cpu_baseline, --impl reference, and torch_gpu_baseline - the
+same op sequence on the B200 as the like-for-like PyTorch baseline of SURVEY 8(d)) may import this module; the
 package aaclip_b200 never does.
 
 Pinning: the reference ships no tests and no golden vectors, so the restatement is pinned
@@ -159,7 +160,7 @@ def gaussian_blur2d(x: torch.Tensor, kernel_size: Tuple[int, int], sigma: Tuple[
     gy, gx = gaussian_kernel1d(ky, sigma[1]), gaussian_kernel1d(kx, sigma[0])
     b, c, h, w = x.shape
     xp = F.pad(x, (kx // 2, kx // 2, ky // 2, ky // 2), mode="reflect")
-    k2d = torch.outer(gy, gx).to(x.dtype)[None, None].expand(c, 1, ky, kx)
+    k2d = torch.outer(gy, gx).to(device=x.device, dtype=x.dtype)[None, None].expand(c, 1, ky, kx)
     return F.conv2d(xp, k2d, groups=c)
 
 

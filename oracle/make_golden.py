@@ -186,6 +186,31 @@ def main():
     torch.save({"seed": 123, "old_grid": 24, "new_grid": 37, "width": 64,
                 "resized": sd_ref["visual.positional_embedding"].clone()}, os.path.join(out_dir, "pos_embed_24_to_37.pt"))
 
+    # ---- checkpoint ingestion: an OpenAI-layout fp16 state dict through the reference's own loading chain
+    #      (model/openai.py:66-77 -> model/model.py:311-368 -> model/clip.py:112-131), at a different target resolution
+    import hashlib
+    from model.model import CLIP as RefCLIP, build_model_from_openai_state_dict
+    from aaclip_b200.clip import load_openai_state_dict
+    tiny = synth.ModelCfg(**synth.OPENAI_TINY)
+    target = 98   # 7 x 7 grid from the checkpoint's 4 x 4
+    pre = build_model_from_openai_state_dict(synth.openai_style_state_dict(tiny, 7)).float()   # load_openai_model, fp32
+    sd_pre = pre.state_dict()
+    ref_model = RefCLIP(embed_dim=tiny.embed_dim,
+                        vision_cfg={"image_size": target, "layers": tiny.layers, "width": tiny.width, "patch_size": tiny.patch_size},
+                        text_cfg={"context_length": tiny.t_context, "vocab_size": tiny.t_vocab, "width": tiny.t_width,
+                                  "heads": tiny.t_heads, "layers": tiny.t_layers})
+    ref_resize(sd_pre, ref_model)
+    ref_model.load_state_dict(sd_pre, strict=True)
+    ref_sd = {k: v.detach().float().contiguous() for k, v in ref_model.state_dict().items()}
+    ours = load_openai_state_dict(synth.openai_style_state_dict(tiny, 7), img_size=target)
+    our_sd = {k: v.detach().float().contiguous() for k, v in ours.state_dict().items()}
+    assert set(ref_sd) == set(our_sd), set(ref_sd) ^ set(our_sd)
+    report["openai_ingest_maxdiff"] = max(maxdiff(ref_sd[k], our_sd[k]) for k in ref_sd)
+    torch.save({"cfg": synth.OPENAI_TINY, "seed": 7, "target_image_size": target,
+                "sha256": {k: hashlib.sha256(v.numpy().tobytes()).hexdigest() for k, v in ref_sd.items()},
+                "visual.positional_embedding": ref_sd["visual.positional_embedding"].clone()},
+               os.path.join(out_dir, "openai_ingest_tiny.pt"))
+
     json.dump(report, open(os.path.join(out_dir, "oracle_vs_reference.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))
     bad = {k: v for k, v in report.items() if not v < 2e-4}

@@ -240,3 +240,89 @@ def test_effective_levels_follow_the_reference_membership_test():
     assert effective_levels([12, 6, 6, 24, 18, 12], 24) == [6, 12, 18, 24]
     assert effective_levels([0, 6, 25, 24, -3], 24) == [6, 24]
     assert effective_levels([30], 24) == []
+
+
+def test_openai_state_dict_ingestion_vs_reference_golden():
+    """(f)3: an OpenAI-layout checkpoint (fp16 Linear / Conv / attention tensors, metadata scalars) through
+    aaclip_b200.clip.load_openai_state_dict equals, tensor for tensor and bit for bit, what the reference's own chain
+    (load_openai_model -> build_model_from_openai_state_dict -> .float() -> CLIP(**json, image_size) -> resize_pos_embed ->
+    load_state_dict; golden written by oracle/make_golden.py from the real reference) leaves in the model."""
+    import hashlib
+    from aaclip_b200.clip import cfg_from_openai_state_dict, load_openai_state_dict
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "openai_ingest_tiny.pt"), weights_only=False)
+    cfg = synth.ModelCfg(**g["cfg"])
+    sd16 = synth.openai_style_state_dict(cfg, g["seed"])
+    assert sd16["visual.transformer.resblocks.0.attn.in_proj_weight"].dtype == torch.float16
+    assert sd16["visual.ln_pre.weight"].dtype == torch.float32 and "input_resolution" in sd16
+    inferred = cfg_from_openai_state_dict(sd16)
+    assert (inferred.width, inferred.layers, inferred.patch_size, inferred.image_size, inferred.heads) == (128, 2, 14, 56, 2)
+    assert (inferred.t_width, inferred.t_heads, inferred.t_layers, inferred.t_vocab, inferred.embed_dim) == (64, 1, 2, 128, 32)
+    model = load_openai_state_dict(sd16, img_size=g["target_image_size"])
+    got = {k: v.detach().float().contiguous() for k, v in model.state_dict().items()}
+    assert set(got) == set(g["sha256"])
+    assert all(v.dtype == torch.float32 for v in model.state_dict().values() if torch.is_floating_point(v))
+    bad = [k for k, v in got.items() if hashlib.sha256(v.numpy().tobytes()).hexdigest() != g["sha256"][k]]
+    assert not bad, bad
+    assert torch.equal(got["visual.positional_embedding"], g["visual.positional_embedding"])
+    assert got["visual.positional_embedding"].shape[0] == (g["target_image_size"] // 14) ** 2 + 1
+    # the wrapped form model/openai.py:70-72 also accepts: {"state_dict": {"module.<key>": tensor}}
+    wrapped = {"state_dict": {"module." + k: v for k, v in sd16.items()}}
+    again = load_openai_state_dict(wrapped, img_size=g["target_image_size"])
+    assert all(torch.equal(a, b) for a, b in zip(again.state_dict().values(), model.state_dict().values()))
+    with pytest.raises(ValueError):
+        load_openai_state_dict({k: v for k, v in sd16.items() if k != "visual.proj"})
+
+
+REFERENCE = os.environ.get("AACLIP_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "model")), reason="the reference tree is not on this machine")
+def test_reference_clip_object_maps_onto_engine_weights():
+    """Drop-in guard: the REAL reference CLIP(**ViT-L-14-336.json), built on the meta device (no
+    memory, no init), wrapped in aaclip_b200.AdaptedCLIP: the architecture the engine infers is exactly VIT_L_14_336 and
+    every tensor the engine wants (weight_map) is one the reference module tree actually has, with the expected shape."""
+    import importlib
+    import json
+    import types
+    for name in ("ipdb", "ftfy"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["ftfy"].fix_text = getattr(sys.modules["ftfy"], "fix_text", lambda t: t)
+    sys.path.insert(0, REFERENCE)
+    try:
+        from model.model import CLIP as RefCLIP
+        jcfg = json.load(open(os.path.join(REFERENCE, "model/model_configs/ViT-L-14-336.json")))
+        with torch.device("meta"):
+            ref_clip = RefCLIP(**jcfg)
+        from aaclip_b200.adapter import AdaptedCLIP, _infer_cfg, effective_levels
+        model = AdaptedCLIP(clip_model=ref_clip, text_adapt_weight=0.1, image_adapt_weight=0.1, text_adapt_until=3,
+                            image_adapt_until=6, levels=[6, 12, 18, 24], relu=False)
+        cfg = _infer_cfg(ref_clip, effective_levels(model.levels, 24), 6, 3, 0.1, 0.1, False)
+        want = synth.VIT_L_14_336
+        for f in ("image_size", "patch_size", "width", "layers", "heads", "mlp_width", "embed_dim", "quick_gelu", "t_context",
+                  "t_vocab", "t_width", "t_heads", "t_layers", "levels", "image_adapt_until", "text_adapt_until", "relu"):
+            assert getattr(cfg, f) == getattr(want, f), f
+        from aaclip_b200.engine import weight_map
+        wm = weight_map(cfg)
+        sources = dict(model._named_sources())
+        missing = [k for k in wm if k not in sources]
+        assert not missing, missing[:5]
+        assert tuple(sources["clip.visual.conv1.weight"].shape) == (1024, 3, 14, 14)
+        assert tuple(sources["clip.visual.positional_embedding"].shape) == (577, 1024)
+        assert tuple(sources["clip.visual.transformer.resblocks.23.attn.in_proj_weight"].shape) == (3072, 1024)
+        assert tuple(sources["clip.transformer.resblocks.11.mlp.c_fc.weight"].shape) == (3072, 768)
+        assert tuple(sources["image_adapter.seg_proj.3.fc.weight"].shape) == (768, 1024)
+        assert tuple(sources["text_adapter.3.fc.0.weight"].shape) == (768, 768)
+    finally:
+        sys.path.remove(REFERENCE)
+        for m in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
+            del sys.modules[m]
+
+
+def test_container_block_forward_raises_clearly():
+    from aaclip_b200.clip import CLIP
+    blk = CLIP(synth.tiny_cfg(), text=False).visual.transformer.resblocks[0]
+    with pytest.raises(NotImplementedError, match="CUDA engine"):
+        blk(torch.zeros(5, 1, 256))

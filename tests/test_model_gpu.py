@@ -615,3 +615,100 @@ def test_ln_fold_with_large_row_mean_vs_oracle(offset):
             assert e_seg <= SEG_TOL and e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
         finally:
             eng.close()
+
+
+@pytest.mark.parametrize("scale", [60.0])
+def test_outlier_channels_full_depth_both_ln_schedules_vs_oracle(scale):
+    """Trained CLIP ViT-L carries a few 'massive activation' channels, tens of times larger than the rest of the residual
+    stream from the first blocks to the last.  Random-init statistics do not: emulate them - three channels get an ln_pre
+    gain of x`scale`, an ln_pre offset and a c_proj bias of +-`scale` in blocks 1 and 2 - and run the FULL 24-layer model.
+    The folded schedule feeds bf16(x) (not bf16(LN(x))) to the tensor core and takes the variance as E[x^2] - mean^2 from
+    per-slice sums; the separate schedule normalises first.  Both must hold the north-star tolerances against the fp32
+    oracle, and the image ranking must be identical."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.VIT_L_14_336
+    sd, ia = dict(synth.clip_state_dict(cfg, 0, text=False)), synth.image_adapter_state_dict(cfg, 0)
+    ch = torch.tensor([7, 300, 777])
+    sign = torch.tensor([1.0, -1.0, 1.0])
+    for key in ("visual.ln_pre.weight", "visual.ln_pre.bias", "visual.transformer.resblocks.1.mlp.c_proj.bias",
+                "visual.transformer.resblocks.2.mlp.c_proj.bias"):
+        sd[key] = sd[key].clone()
+    sd["visual.ln_pre.weight"][ch] *= scale
+    sd["visual.ln_pre.bias"][ch] += 0.5 * scale * sign
+    sd["visual.transformer.resblocks.1.mlp.c_proj.bias"][ch] += scale * sign
+    sd["visual.transformer.resblocks.2.mlp.c_proj.bias"][ch] -= 0.5 * scale * sign
+    img, T = synth.images(3, cfg, seed=29), synth.anchors(cfg, seed=1)
+    with torch.no_grad():
+        seg_o, det_o = orc.visual_forward(sd, ia, img)
+        map_o, score_o = orc.predict(seg_o, det_o, T, cfg.image_size, "Industrial")
+    for fold in (True, False):
+        eng = Engine(cfg, device=0, max_batch=3, text=False, ln_fold=fold)
+        try:
+            eng.load_state_dicts(sd, ia, None)
+            seg, det = eng.visual_forward(img.cuda())
+            maps, scores = eng.forward_fused(img.cuda(), T.cuda())
+            torch.cuda.synchronize()
+            e_seg = max((a.cpu() - b).abs().max().item() for a, b in zip(seg, seg_o))
+            e_det = (det.cpu() - det_o).abs().max().item()
+            e_map = (_mm(maps.cpu()) - _mm(map_o)).abs().max().item()
+            e_sc = (scores.cpu() - score_o).abs().max().item()
+            print(f"[outlier channels x{scale:.0f}, ln_fold={fold}] seg {e_seg:.3e} det {e_det:.3e} normalised map {e_map:.3e} "
+                  f"score {e_sc:.3e}")
+            assert e_seg <= SEG_TOL and e_det <= SEG_TOL and e_map <= MAP_NORM_TOL and e_sc <= SCORE_TOL
+            assert torch.equal(scores.cpu().argsort(), score_o.argsort())
+        finally:
+            eng.close()
+
+
+def test_openai_checkpoint_through_the_drop_in(full):
+    """(f)3 end to end: a ViT-L/14-336 checkpoint in the OpenAI archive's layout (fp16 tensors, metadata scalars) ->
+    load_openai_state_dict -> AdaptedCLIP -> maps, against the engine loaded directly with the same values (the fp16
+    tensors widened to fp32): bit-identical, because both paths hand the engine the same fp32 numbers."""
+    from aaclip_b200 import synth
+    from aaclip_b200.adapter import AdaptedCLIP
+    from aaclip_b200.clip import load_openai_state_dict
+    from aaclip_b200.engine import Engine
+    cfg, _, _, ia, _ = full
+    sd16 = synth.openai_style_state_dict(cfg, 5)
+    clip = load_openai_state_dict(sd16)
+    model = AdaptedCLIP(clip_model=clip, relu=False, max_batch=2).to("cuda").eval()
+    model.image_adapter.load_state_dict(ia)
+    img, T = synth.images(2, cfg, seed=3).cuda(), synth.anchors(cfg, seed=1).cuda()
+    maps, scores = model.predict(img, T, "Industrial")
+    eng = Engine(cfg, device=0, max_batch=2, text=False)
+    try:
+        eng.load_state_dicts({k: (v.float() if torch.is_floating_point(v) else v) for k, v in sd16.items()}, ia, None)
+        m2, s2 = eng.forward_fused(img, T)
+        torch.cuda.synchronize()
+        assert torch.equal(maps, m2) and torch.equal(scores, s2)
+    finally:
+        eng.close()
+        model._engine.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """Contexts on two GPUs of one process (the > 48 KB shared-memory opt-in is per device context, and a
+    stream handle is only valid on its own device): same weights, same inputs, same results, with the thread's current
+    device left where the caller had it."""
+    from aaclip_b200 import ops, synth
+    from aaclip_b200.engine import Engine
+    cfg = synth.ModelCfg(layers=3, t_layers=0, image_adapt_until=2, levels=[1, 2, 3])
+    sd, ia = synth.clip_state_dict(cfg, 0, text=False), synth.image_adapter_state_dict(cfg, 0)
+    img, T = synth.images(2, cfg, seed=1), synth.anchors(cfg, seed=1)
+    torch.cuda.set_device(0)
+    outs = []
+    for dev in (0, 1):
+        eng = Engine(cfg, device=dev, max_batch=2, text=False)
+        eng.load_state_dicts(sd, ia, None)
+        assert torch.cuda.current_device() == 0
+        seg, det = eng.visual_forward(img.to(f"cuda:{dev}"))
+        maps, scores = eng.forward_fused(img.to(f"cuda:{dev}"), T.to(f"cuda:{dev}"))
+        head, _ = ops.anomaly_head(seg, T.to(f"cuda:{dev}"), cfg.image_size, ops.HEAD_TEST_INDUSTRIAL)
+        torch.cuda.synchronize(dev)
+        assert torch.cuda.current_device() == 0
+        outs.append((maps.cpu(), scores.cpu(), head.cpu()))
+        eng.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])

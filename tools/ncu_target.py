@@ -1,6 +1,10 @@
-"""Small, fixed launch sequence for ncu captures (one launch list + one --set full capture per change):
-  3 x head_stream (bf16, 4 levels, B=64)   3 x out_proj residual GEMM   2 x c_proj residual GEMM   2 x attention (B=64)
-Inputs rotate so every launch streams from HBM.  Usage: python tools/ncu_target.py [head] [gemm] [attn]"""
+"""Small, fixed launch sequence for ncu captures (one launch list + one --set full capture per change), at the bench
+shapes (B = 64, M = 64 x 577), inputs rotating so every launch streams from HBM:
+  head : 3 x aaclip_anomaly_head (bf16, 4 levels)  -> head_stream_kernel + maps_from_dots_kernel
+  gemm : 2 x in_proj (ln_1 folded) | 2 x out_proj (residual + statistics) | 2 x c_fc (ln_2 folded, erf-GELU) |
+         2 x c_proj (residual + statistics)          <- tools/ncu_traffic.py relies on this order
+  attn : 2 x attention
+Usage: python tools/ncu_target.py [head] [gemm] [attn]"""
 import sys
 
 import torch
@@ -22,15 +26,25 @@ if "head" in what:
     torch.cuda.synchronize()
     del sets
 if "gemm" in what:
-    for K, reps in ((1024, 3), (4096, 2)):
-        a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
-        w = (torch.randn(1024, K, device="cuda") * 0.03).to(torch.bfloat16)
-        bias = torch.randn(1024, device="cuda")
-        xs = [torch.randn(M, 1024, device="cuda") for _ in range(3)]
-        for i in range(reps):
-            ops.gemm_resid_ln(a, w, bias, xs[i % 3])
+    xs = [torch.randn(M, 1024, device="cuda") for _ in range(3)]
+    g, bta = torch.randn(1024, device="cuda") * 0.1 + 1, torch.randn(1024, device="cuda") * 0.1
+    xb, part = ops.rowstats_cast(xs[0], 8)
+    for N, K, kind in ((3072, 1024, "lnfold"), (1024, 1024, "resid"), (4096, 1024, "lnfold_gelu"), (1024, 4096, "resid")):
+        w32 = torch.randn(N, K, device="cuda") * 0.03
+        bias = torch.randn(N, device="cuda")
+        if kind.startswith("lnfold"):
+            wf, cs, bf = ops.fold_ln_weight(w32, bias, g, bta)
+            for i in range(2):
+                ops.gemm_lnfold(xb, wf, bf, cs, part, act=ops.ACT_GELU_ERF if kind.endswith("gelu") else ops.ACT_NONE)
+        else:
+            a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+            w = w32.to(torch.bfloat16)
+            for i in range(2):
+                ops.gemm_resid_ln(a, w, bias, xs[i % 3])
+            del a, w
         torch.cuda.synchronize()
-        del a, w, xs
+        del w32
+    del xs
 if "attn" in what:
     qkvs = [(torch.randn(M, 3072, device="cuda") * 1.5).to(torch.bfloat16) for _ in range(2)]
     for i in range(2):
