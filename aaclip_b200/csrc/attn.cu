@@ -109,7 +109,7 @@ template <bool TRACE_ON, int POLY, int MINB, int NQ, int BAL, int DEEP>
 __global__ void __launch_bounds__(BAL ? THREADS_BAL : THREADS, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                  const __grid_constant__ CUtensorMap tmO, int L, int heads, int causal, int n_items, int n_qt,
-                 long long* trace, int trace_cta, float rescale_log2) {
+                 long long* trace, int trace_cta, const float RESCALE_MAX) {
   using LY = Lay<NQ>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-B alignment
@@ -277,14 +277,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t t_lane = tmem_base + ((quarter * 32u) << 16);
     const uint32_t t_o = t_lane + 2u * BKV;
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    const float RESCALE_MAX = exp2f(rescale_log2); // lazy rescale: tolerate p (and tile row sums) up to 2^8 before touching O
+    // RESCALE_MAX (a kernel parameter: read from the constant bank, no register): lazy rescale - p and tile row sums may
+    // reach 2^8 before O is touched
     uint8_t* p_row = smem + LY::OFF_P + row * 128;
     uint8_t* p_warp = smem + LY::OFF_P + quarter * 32u * 128u;   // this warp's 32 rows x 128 B (output staging)
     const uint32_t sw = uint32_t(row & 7);
     // shared-space address of the 16-B chunk that holds keys [8c, 8c+8) of this row's P line (128B swizzle)
-    uint32_t p_addr[8];
+    // Chunks 0..3 of the row hold the tile's keys when g is even, 4..7 when it is odd: (ch + 4) ^ sw == (ch ^ sw) ^ 4, so
+    // the odd tile's addresses are the even tile's with bit 6 flipped (the row is 128-byte aligned) - four registers
+    // and one XOR per store instead of eight addresses the compiler rebuilt every tile (20 instructions of 147).
+    uint32_t p_addr[4];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) p_addr[ch] = ptx::smem_u32(p_row) + ((uint32_t(ch) ^ sw) << 4);
+    for (int ch = 0; ch < 4; ++ch) p_addr[ch] = ptx::smem_u32(p_row) + ((uint32_t(ch) ^ sw) << 4);
     uint32_t sv[BKV];                              // raw scores of the current tile (this thread's row)
 
     auto load_scores = [&](uint32_t g) { ptx::tmem_ld_32x32b_x32(t_lane + (g & 1u) * uint32_t(BKV), sv); };
@@ -318,7 +322,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         ptx::fadd2(b0, b1, e[4], e[5], e[6], e[7]);
         ptx::fadd2(a0, a1, a0, a1, b0, b1);
         ptx::fadd2(r0, r1, r0, r1, a0, a1);
-        const uint32_t a = half ? p_addr[4 + g8] : p_addr[g8];
+        const uint32_t a = p_addr[g8] ^ (half << 6);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ptx::pack_bf16x2(e[0], e[1])),
                      "r"(ptx::pack_bf16x2(e[2], e[3])), "r"(ptx::pack_bf16x2(e[4], e[5])),
                      "r"(ptx::pack_bf16x2(e[6], e[7])) : "memory");
@@ -452,6 +456,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         ++g;
       };
 
+      // A warp whose 32 query rows all lie past the sequence end (L = 577: the fourth warp of every image's fifth query
+      // tile, 5 % of the warp-tiles; a third of the text tower's) computes nothing that is ever stored: it keeps the
+      // barrier protocol (wait for the next S tile, take it from TMEM so that a following live item finds its first
+      // scores in registers, hand the P slot over) and skips the exponentials, the P stores and the output tile.  Its P
+      // rows keep stale finite values: the rows of O they feed are never stored either.
+      if (it.q0 + int(quarter) * 32 >= L) {
+#pragma unroll 1
+        for (int j = 0; j < it.n_kv; ++j) {
+          const uint32_t half = g & 1u;
+          if (j + 1 < it.n_kv || more_items) {
+            ptx::mbar_wait(&bars->s_full[half ^ 1u], ((g + 1) >> 1) & 1u);
+            ptx::tc_fence_after();
+            load_scores(g + 1);
+            ptx::tmem_ld_wait();
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars->p_full[half]);
+          ++g;
+        }
+        continue;
+      }
+
       int j = 0;
       tile(std::false_type{}, j++);
 #pragma unroll 1
@@ -577,7 +604,7 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
   const int sms = host::sm_count(dev);
   const int grid = (int)std::min<long long>(items, (long long)v.ctas_per_sm * (sms > 0 ? sms : 148));
   AACLIP_CUDA_CHECK(host::launch(v.fn, dim3(grid), dim3(v.threads), (size_t)v.smem, stream, tmQ, tmKV, tmO, L, heads,
-                                 causal, (int)items, n_qt, g_trace, g_trace_cta, rescale));
+                                 causal, (int)items, n_qt, g_trace, g_trace_cta, exp2f(rescale)));
   return host::OK;
 }
 

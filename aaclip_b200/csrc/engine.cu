@@ -110,7 +110,7 @@ struct aaclip_ctx {
   aaclip_cfg cfg;
   int device = 0;
   int G = 0, P = 0, L = 0, Kpad = 0, E = 0;
-  int cta_group = 2;
+  int cta_group = 0;   // 0: tile shape chosen per launch (k::launch_gemm); 1 / 2 / 3 force one
   // LayerNorm folded into the consumer GEMMs of the visual tower (see gemm_sm100.cuh); AACLIP_LN_FOLD=0 disables it
   bool ln_fold = true, fold_dirty = true;
   float2* part = nullptr;   // [rows][width / 128] (sum, sum of squares) per 128-column slice of the fp32 rows
@@ -423,7 +423,7 @@ extern "C" int aaclip_create(aaclip_ctx** out, const aaclip_cfg* cfg, int device
   aaclip_ctx* c = new aaclip_ctx();
   c->cfg = *cfg;
   c->device = device;
-  c->cta_group = (cfg->cta_group == 1 || cfg->cta_group == 2) ? cfg->cta_group : 2;
+  c->cta_group = (cfg->cta_group >= 1 && cfg->cta_group <= 3) ? cfg->cta_group : 0;
   c->G = cfg->image_size / cfg->patch_size;
   c->P = c->G * c->G;
   c->L = c->P + 1;

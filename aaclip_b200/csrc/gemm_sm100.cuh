@@ -61,14 +61,17 @@ struct Args {
 // RLN: the OUT_F32_RESID_LN epilogue (64 KB of x_old ring, one stage fewer); RV selects its variant (see
 // epilogue_resid_ln): the working epilogue warps (8: two per TMEM lane quarter, 128 columns each; 4: one per quarter, all
 // 256 columns) and the depth of each warp's x_old ring.
-template <int CG, bool RLN = false, int RV = 0>
+// BN_: tile N.  256 is the throughput shape; 128 (CG = 1 only) halves the work per tile and k-block for launches whose
+// tiles would not fill the SMs (small batches: the K loop of one tile is a serial chain).
+template <int CG, bool RLN = false, int RV = 0, int BN_ = 256>
 struct Cfg {
+  static_assert(BN_ == 256 || (BN_ == 128 && CG == 1), "tile N: 256, or 128 with cta_group 1");
   static constexpr int BM = 128;           // accumulator rows per CTA (== TMEM lanes)
-  static constexpr int BN = 256;           // tile N (per CTA pair when CG == 2)
+  static constexpr int BN = BN_;           // tile N (per CTA pair when CG == 2)
   static constexpr int BN_CTA = BN / CG;   // rows of W staged by each CTA
   static constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
   static constexpr int UMMA_K = 16;
-  static constexpr int STAGES = RLN ? ((CG == 1) ? 3 : 5) : ((CG == 1) ? 4 : 6);
+  static constexpr int STAGES = (BN_ == 128) ? (RLN ? 5 : 6) : RLN ? ((CG == 1) ? 3 : 5) : ((CG == 1) ? 4 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -76,13 +79,13 @@ struct Cfg {
   static constexpr int NUM_EPI_WARPS = 8;
   // RLN: only 4 of the 8 epilogue warps work (one per TMEM lane quarter, all 256 columns of its 32 rows), each with a
   // ring of XRING x_old chunks: what bounds that epilogue is bytes in flight per SM, not issue slots
-  static constexpr int ACTIVE_EPI_WARPS = (RLN && RV != 1 && RV != 4) ? 4 : 8;
+  static constexpr int ACTIVE_EPI_WARPS = (BN_ == 128 || (RLN && RV != 1 && RV != 4)) ? 4 : 8;
   static constexpr int XRING = RV == 1 ? 1 : RV == 2 ? 3 : RV == 4 ? 2 : 4;
   static constexpr int STAGING_BYTES = (RLN ? 2 : 1) * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + NUM_EPI_WARPS * STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int THREADS = 128 + NUM_EPI_WARPS * 32;
-  static constexpr int TMEM_COLS = 512;    // 2 accumulator buffers x 256 fp32 columns
+  static constexpr int TMEM_COLS = 2 * BN; // 2 accumulator buffers x BN fp32 columns
 };
 
 // erf-GELU via Abramowitz-Stegun 7.1.26 (|erf err| <= 1.5e-7): 0.5x(1+erf(x/sqrt2)) = hx + |hx| * erf(|x|/sqrt2),
@@ -491,11 +494,11 @@ __device__ __forceinline__ void epilogue_dots(uint32_t t_addr, int row0, int col
   if (row < a.M) a.partials[size_t(row) * (a.dots_cols >> 7) + (col0 >> 7)] = make_float4(ss, d0, d1, 0.f);
 }
 
-template <int CG, int ACT, int OUT, int LNF = 0, int RV = 0>
+template <int CG, int ACT, int OUT, int LNF = 0, int RV = 0, int BN = 256>
 __global__ void __launch_bounds__(Cfg<CG>::THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const Args args) {
-  using C = Cfg<CG, OUT == OUT_F32_RESID_LN, RV>;
+  using C = Cfg<CG, OUT == OUT_F32_RESID_LN, RV, BN>;
   extern __shared__ uint8_t smem_raw[];
   // identical offset in both CTAs of a pair: the dynamic smem window starts at the same address
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -616,7 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* stage = staging + warp * (C::NUM_EPI_WARPS / C::ACTIVE_EPI_WARPS) * C::STAGING_BYTES;
     uint32_t it = 0;
     // RLN: x_old chunk jj of this warp's chunk stream (NCH per tile, tiles in this CTA's order) -> ring slot jj % XRING
-    constexpr int NCH = 32 / C::ACTIVE_EPI_WARPS;   // 32-column chunks per warp and tile: 8 (4 warps) / 4 (8 warps)
+    constexpr int NCH = C::BN / (8 * C::ACTIVE_EPI_WARPS);   // 32-column chunks per warp and tile (BN 256: 8 with 4 warps, 4 with 8)
     [[maybe_unused]] uint32_t xj = 0, xphase = 0;
     [[maybe_unused]] uint64_t* xb = &xbar[warp * C::XRING];
     [[maybe_unused]] auto request_x = [&](uint32_t jj) {

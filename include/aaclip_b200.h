@@ -108,7 +108,8 @@ typedef struct {
   /* capacity */
   int max_batch;    /* images per visual forward the workspaces are sized for */
   int max_text;     /* sentences per text forward */
-  int cta_group;    /* 1 or 2: tcgen05 cta_group used by the GEMMs (0 = library default) */
+  int cta_group;    /* GEMM tile shape: 0 = chosen per launch (wave model); 1 = cta_group::1, 128x256 tiles; 2 = cta_group::2
+                       CTA pairs, 256x256 tiles; 3 = cta_group::1, 128x128 tiles (small batches) */
   int ln_fold;      /* visual tower: 0 = library default (on, AACLIP_LN_FOLD=0 turns it off), 1 = fold ln_1 / ln_2 into
                        the in_proj / c_fc GEMMs (no LayerNorm launches inside the blocks), 2 = separate LayerNorm kernels */
 } aaclip_cfg;
@@ -220,7 +221,8 @@ int aaclip_text_forward(aaclip_ctx* ctx, const int32_t* tokens, int n, float* ou
 int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int col, void* stream);
 
 /* ---- building blocks (exported so the parity tests can pin each kernel on its own) ------------------ */
-/* out = epilogue(A[M,K] . W[N,K]^T), bf16 operands (pitches lda/ldw elements), fp32 accumulation. */
+/* out = epilogue(A[M,K] . W[N,K]^T), bf16 operands (pitches lda/ldw elements), fp32 accumulation.
+ * cta_group: tile shape as in aaclip_cfg (0 = chosen from M, N and the SM count). */
 int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                      void* out, int ldo, int act, int out_mode, const float* pos, int P, int cta_group, void* stream);
 /* The folded-LayerNorm schedule of the visual tower (LN(x) W^T + b == rstd (x (W o gamma)^T - mean s) + b'): the

@@ -87,7 +87,7 @@ def visual_forward(clip_sd: SD, image_adapter_sd: SD, image: torch.Tensor, *, pa
     sd = clip_sd
     x = F.conv2d(image, sd["visual.conv1.weight"], stride=patch_size)          # :68
     x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)                 # :69-70
-    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype)
+    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype, device=x.device)
     x = torch.cat([cls, x], dim=1)                                             # :72-81
     x = x + sd["visual.positional_embedding"]                                  # :82
     x = layer_norm(x, sd, "visual.ln_pre.")                                    # :84-85 (patch_dropout = identity)
@@ -121,13 +121,13 @@ def encode_text(clip_sd: SD, text_adapter_sd: SD, tokens: torch.Tensor, *, heads
     sd = clip_sd
     x = F.embedding(tokens.long(), sd["token_embedding.weight"])               # :118
     x = x + sd["positional_embedding"]                                         # :122
-    mask = causal_mask(tokens.shape[1])
+    mask = causal_mask(tokens.shape[1]).to(x.device)
     for i in range(layers):                                                    # :125-136
         x = residual_attention_block(x, sd, f"transformer.resblocks.{i}.", heads, quick_gelu, mask)
         if i < text_adapt_until:
             x = adapter_mix(x, text_adapter_sd[f"{i}.fc.0.weight"], text_adapt_weight)
     x = layer_norm(x, sd, "ln_final.")                                         # :138
-    eot = x[torch.arange(x.shape[0]), tokens.argmax(dim=-1)]                   # :140
+    eot = x[torch.arange(x.shape[0], device=x.device), tokens.argmax(dim=-1)]                   # :140
     return F.leaky_relu(F.linear(eot, text_adapter_sd[f"{text_adapt_until}.fc.0.weight"]), 0.01)
 
 

@@ -41,7 +41,7 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_plain_f32(cg, M, N, K):
     ops = _ops()
@@ -54,7 +54,7 @@ def test_gemm_plain_f32(cg, M, N, K):
     assert rel < 2e-3
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 def test_gemm_identity_layout(cg):
     """W = identity-like selector: output must reproduce A's columns exactly (catches descriptor/swizzle bugs)."""
     ops = _ops()
@@ -66,7 +66,7 @@ def test_gemm_identity_layout(cg):
     assert torch.equal(out, a.float())
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 @pytest.mark.parametrize("act", ["none", "gelu_erf", "quick_gelu"])
 def test_gemm_bias_act_bf16(cg, act):
     ops = _ops()
@@ -85,7 +85,7 @@ def test_gemm_bias_act_bf16(cg, act):
     assert bool((err <= tol).all())
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 def test_gemm_residual_f32(cg):
     ops = _ops()
     M, N, K = 1154, 1024, 4096
@@ -101,7 +101,7 @@ def test_gemm_residual_f32(cg):
     assert rel < 2e-3
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 def test_gemm_leaky_f32(cg):
     ops = _ops()
     M, N, K = 577, 1024, 1024
@@ -114,7 +114,7 @@ def test_gemm_leaky_f32(cg):
     assert rel < 2e-3
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 def test_gemm_patch_scatter(cg):
     ops = _ops()
     B, P, N, K = 3, 576, 1024, 640
@@ -202,7 +202,7 @@ def test_map_minmax(B, n):
 
 
 # ------------------------------------------------------------------------------------------------ folded LayerNorm
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 @pytest.mark.parametrize("M,K", [(1154, 1024), (300, 4096)])
 def test_gemm_resid_ln(cg, M, K):
     """Residual GEMM of the folded-LayerNorm schedule: x += A W^T + b through TMA load / store, bf16 copy, partial sums."""
@@ -243,7 +243,7 @@ def test_fold_ln_weight_and_rowstats():
     assert bool((part[:, 1:] == 0).all())
 
 
-@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("cg", [1, 2, 3, 0])
 @pytest.mark.parametrize("act", ["none", "gelu_erf"])
 @pytest.mark.parametrize("row_mean", [0.0, 2.0])
 def test_gemm_lnfold_vs_layernorm_linear(cg, act, row_mean):
