@@ -609,6 +609,7 @@ int k::launch_attention(const void* qkv, void* out, int B, int L, int heads, int
 }
 
 extern "C" int aaclip_attention(const void* qkv, void* out, int B, int L, int heads, int causal, void* stream) {
+  host::PointerDeviceGuard dev_guard(qkv);
   return k::launch_attention(qkv, out, B, L, heads, causal, static_cast<cudaStream_t>(stream));
 }
 
@@ -617,6 +618,7 @@ extern "C" int aaclip_attention(const void* qkv, void* out, int B, int L, int he
 // trace[slot * 32 + tile] (device memory, >= 24 * 32 int64).  Used to study the pipeline; not part of the hot path.
 extern "C" int aaclip_attention_trace(const void* qkv, void* out, int B, int L, int heads, int causal, long long* trace,
                                       int cta, void* stream) {
+  host::PointerDeviceGuard dev_guard(qkv);
   g_trace = trace; g_trace_cta = cta;
   int rc = k::launch_attention(qkv, out, B, L, heads, causal, static_cast<cudaStream_t>(stream));
   g_trace = nullptr; g_trace_cta = -1;

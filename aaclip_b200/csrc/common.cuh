@@ -127,6 +127,26 @@ inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// The context-free entry points (building blocks, head, loader transform) run on the device that owns their first
+// device pointer and give the caller's current device back on return: a stream handle and a kernel's shared-memory
+// opt-in belong to one device, and the thread's current device belongs to the caller (PyTorch).
+struct PointerDeviceGuard {
+  int prev = -1, dev = -1;
+  explicit PointerDeviceGuard(const void* p) {
+    cudaPointerAttributes at;
+    if (p != nullptr && cudaPointerGetAttributes(&at, p) == cudaSuccess &&
+        (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
+      dev = at.device;
+    else
+      cudaGetLastError();   // host / unregistered pointer: stay on the current device (argument checks report it)
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~PointerDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  PointerDeviceGuard(const PointerDeviceGuard&) = delete;
+  PointerDeviceGuard& operator=(const PointerDeviceGuard&) = delete;
+};
+
 inline int sm_count(int device) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device]) return cached[device];

@@ -159,6 +159,7 @@ int k::launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N,
 extern "C" int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                                 const float* bias, void* out, int ldo, int act, int out_mode, const float* pos, int P,
                                 int cta_group, void* stream) {
+  host::PointerDeviceGuard dev_guard(A);
   if (out_mode == gemm::OUT_DOTS) return host::fail(host::ERR_INVALID, "gemm: the dots epilogue is internal to the engine");
   return k::launch_gemm(A, lda, W, ldw, M, N, K, bias, out, ldo, act, out_mode, pos, P, cta_group,
                         static_cast<cudaStream_t>(stream));
@@ -169,6 +170,7 @@ extern "C" int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, 
 //   aaclip_gemm_lnfold    out(bf16) <- act(rstd_r (A Wf^T - mean_r colsum) + bias) with the row statistics from part
 extern "C" int aaclip_gemm_resid_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                                     float* x, int ldx, void* xb, int ldxb, void* part_out, int cta_group, void* stream) {
+  host::PointerDeviceGuard dev_guard(A);
   k::LnFold ln;
   ln.xb = xb; ln.ldxb = ldxb; ln.part_out = part_out;
   return k::launch_gemm(A, lda, W, ldw, M, N, K, bias, x, ldx, gemm::ACT_NONE, gemm::OUT_F32_RESID_LN, nullptr, 0, cta_group,
@@ -177,6 +179,7 @@ extern "C" int aaclip_gemm_resid_ln(const void* A, int lda, const void* W, int l
 extern "C" int aaclip_gemm_lnfold(const void* A, int lda, const void* Wf, int ldw, int M, int N, int K, const float* bias,
                                   const float* colsum, const void* part, int slices, float eps, void* out, int ldo, int act,
                                   int cta_group, void* stream) {
+  host::PointerDeviceGuard dev_guard(A);
   k::LnFold ln;
   ln.part_in = part; ln.slices = slices; ln.eps = eps; ln.colsum = colsum;
   return k::launch_gemm(A, lda, Wf, ldw, M, N, K, bias, out, ldo, act, gemm::OUT_BF16, nullptr, 0, cta_group,

@@ -444,6 +444,7 @@ extern "C" int aaclip_anomaly_head(const void* const* seg, int n_levels, int seg
                                    int anchors_batched, const float* det, int B, int P, int E, int img_size, int mode,
                                    float* maps_out, float* scores_out, float* minmax_out, void* workspace,
                                    long long workspace_bytes, void* stream_) {
+  host::PointerDeviceGuard dev_guard((seg != nullptr && n_levels > 0) ? seg[0] : nullptr);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (B <= 0) return host::OK;  // empty batch: nothing to do
   if (!seg || !anchors || n_levels < 1 || n_levels > MAX_LEVELS)
@@ -530,6 +531,7 @@ __global__ void __launch_bounds__(MM_THREADS) map_minmax_kernel(const float* __r
 }  // namespace
 
 extern "C" int aaclip_map_minmax(const float* maps, int B, long long n_pix, float* out, void* stream_) {
+  host::PointerDeviceGuard dev_guard(maps);
   if (B <= 0) return host::OK;
   if (!maps || !out || n_pix <= 0) return host::fail(host::ERR_INVALID, "map_minmax: bad argument");
   map_minmax_kernel<<<B, MM_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(maps, n_pix, out);
@@ -538,6 +540,7 @@ extern "C" int aaclip_map_minmax(const float* maps, int B, long long n_pix, floa
 }
 
 extern "C" int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int col, void* stream_) {
+  host::PointerDeviceGuard dev_guard(emb);
   if (!emb || !anchors || n <= 0 || width <= 0 || (col != 0 && col != 1))
     return host::fail(host::ERR_INVALID, "text_anchor: bad argument");
   text_anchor_kernel<<<1, 256, (n + 8) * sizeof(float), static_cast<cudaStream_t>(stream_)>>>(emb, n, width, anchors, col);

@@ -319,10 +319,12 @@ extern "C" long long aaclip_preprocess_scratch_bytes(int B, int H0, int W0, int 
 
 extern "C" int aaclip_preprocess_u8(const uint8_t* images, int B, int H0, int W0, int S, const float* host_mean,
                                     const float* host_std, uint8_t* scratch, float* out, void* stream) {
+  host::PointerDeviceGuard dev_guard(images);
   return run(images, B, H0, W0, S, host_mean, host_std, scratch, out, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int aaclip_resize_bicubic_u8(const uint8_t* images, int B, int H0, int W0, int S, uint8_t* scratch,
                                         uint8_t* out_u8, void* stream) {
+  host::PointerDeviceGuard dev_guard(images);
   return run(images, B, H0, W0, S, nullptr, nullptr, scratch, nullptr, out_u8, static_cast<cudaStream_t>(stream));
 }

@@ -504,20 +504,24 @@ int k::launch_cast_bf16(const float* x, void* out_bf16, long long n, cudaStream_
 
 extern "C" int aaclip_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
                                 void* out_bf16, float* out_f32, void* stream) {
+  host::PointerDeviceGuard dev_guard(x);
   return k::launch_layernorm(x, gamma, beta, eps, rows, width, 0, 0, 0, out_bf16, out_f32,
                              static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int aaclip_adapter_mix(float* x, const float* a, float w, int rows, int width, void* stream) {
+  host::PointerDeviceGuard dev_guard(x);
   return k::launch_adapter_mix(x, a, w, rows, width, nullptr, nullptr, 0.f, nullptr,
                                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int aaclip_rowstats_cast(const float* x, int rows, int width, void* xb, void* part, int part_slices, void* stream) {
+  host::PointerDeviceGuard dev_guard(x);
   return k::launch_rowstats_cast(x, rows, width, xb, part, part_slices, static_cast<cudaStream_t>(stream));
 }
 extern "C" int aaclip_fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, int N, int K,
                                      void* Wf, float* colsum, float* bias_f, void* stream) {
+  host::PointerDeviceGuard dev_guard(W);
   if (!W || !gamma || !beta || !Wf || !colsum || !bias_f) return host::fail(host::ERR_INVALID, "fold_ln_weight: null argument");
   return k::launch_fold_ln_weight(W, bias, gamma, beta, N, K, Wf, colsum, bias_f, static_cast<cudaStream_t>(stream));
 }

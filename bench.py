@@ -592,17 +592,32 @@ def main():
     # replays each step as one CUDA graph launch (captured the second time a (batch, pointers) key occurs)
     outs = [(torch.empty(B, cfg.image_size, cfg.image_size, device="cuda"), torch.empty(B, device="cuda"))
             for _ in range(n_rot)]
-    gathered = torch.empty(total, device="cuda") if world > 1 else None   # one collective straight into this buffer
+    # N > 1: one NCCL all-gather of the B scores per step, straight into a preallocated buffer, on its own stream behind an
+    # event: the collective of step i rides under the compute of step i + 1, so the ranks meet at the end of the run and
+    # not at every step (a per-step rendezvous on the compute stream makes every step as slow as the slowest rank's)
+    gathered = [torch.empty(total, device="cuda") for _ in range(n_rot)] if world > 1 else None
     side = torch.cuda.Stream()
+    comm = torch.cuda.Stream() if world > 1 else None
     side.wait_stream(torch.cuda.current_stream())
 
+    gather_done = [None] * n_rot   # event of the last gather that read outs[k]'s scores: the forward that rewrites them waits for it
+
     def step(i):
-        maps, scores = eng.forward_fused(inputs[i % n_rot], anchors, "Industrial", out=outs[i % n_rot])
+        k = i % n_rot
+        if world > 1 and gather_done[k] is not None:
+            torch.cuda.current_stream().wait_event(gather_done[k])   # n_rot steps old: never stalls in practice
+        maps, scores = eng.forward_fused(inputs[k], anchors, "Industrial", out=outs[k])
         if world > 1:
-            scores = gather_scores(scores, total, out=gathered)
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                scores = gather_scores(scores, total, out=gathered[k])
+                gather_done[k] = torch.cuda.Event()
+                gather_done[k].record()
         return maps, scores
 
     def sync_all():
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(comm)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -698,11 +713,11 @@ def main():
                 if prev is not None:
                     eng.wait_host(prev)
                     if world > 1:
-                        gather_scores(h_scores[(i - 1) % 2].cuda(non_blocking=True), total, out=gathered)
+                        gather_scores(h_scores[(i - 1) % 2].cuda(non_blocking=True), total, out=gathered[(i - 1) % n_rot])
                 prev = t
             eng.wait_host(prev)
             if world > 1:
-                gather_scores(h_scores[(n - 1) % 2].cuda(non_blocking=True), total, out=gathered)
+                gather_scores(h_scores[(n - 1) % 2].cuda(non_blocking=True), total, out=gathered[(n - 1) % n_rot])
 
         e2e_loop(3)
         sync_all()

@@ -222,7 +222,8 @@ int aaclip_text_anchor(const float* emb, int n, int width, float* anchors, int c
 
 /* ---- building blocks (exported so the parity tests can pin each kernel on its own) ------------------ */
 /* out = epilogue(A[M,K] . W[N,K]^T), bf16 operands (pitches lda/ldw elements), fp32 accumulation.
- * cta_group: tile shape as in aaclip_cfg (0 = chosen from M, N and the SM count). */
+ * cta_group: tile shape, same values as the field of that name in the context configuration (0 = chosen from M, N and the
+ * SM count). */
 int aaclip_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias,
                      void* out, int ldo, int act, int out_mode, const float* pos, int P, int cta_group, void* stream);
 /* The folded-LayerNorm schedule of the visual tower (LN(x) W^T + b == rstd (x (W o gamma)^T - mean s) + b'): the
