@@ -712,3 +712,39 @@ def test_two_devices_in_one_process():
         outs.append((maps.cpu(), scores.cpu(), head.cpu()))
         eng.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_caller_side_stream_capture_joins_the_callers_graph(full):
+    """when the CALLER is capturing the stream (torch.cuda.graph around the forward) the library must not
+    start a nested capture of its own: its launches join the caller's graph, and replaying that graph reproduces the
+    eager result bit for bit - for the fused entry (with extrema) and for the drop-in head."""
+    from aaclip_b200 import ops, synth
+    cfg, eng, *_ = full
+    img = synth.images(2, cfg, seed=41).cuda()
+    T = synth.anchors(cfg, seed=4).cuda()
+    ext_e = torch.empty(2, 2, device="cuda")
+    maps_e, scores_e = eng.forward_fused(img, T, extrema=ext_e)          # eager (also makes sure the weights are folded)
+    seg, det = eng.visual_forward(img, seg_dtype=torch.bfloat16)
+    head_e, hs_e = ops.anomaly_head(seg, T, cfg.image_size, ops.HEAD_TEST_MEDICAL, det=det)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    out = (torch.empty_like(maps_e), torch.empty_like(scores_e))
+    ext = torch.empty_like(ext_e)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        eng.forward_fused(img, T, out=out, extrema=ext)                  # first sight of this key on this stream: eager
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            eng.forward_fused(img, T, out=out, extrema=ext)              # second sight: would be the library's own capture
+            head_g, hs_g = ops.anomaly_head(seg, T, cfg.image_size, ops.HEAD_TEST_MEDICAL, det=det)
+        out[0].zero_(); out[1].zero_(); ext.zero_(); head_g.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], maps_e) and torch.equal(out[1], scores_e) and torch.equal(ext, ext_e)
+    assert torch.equal(head_g, head_e) and torch.equal(hs_g, hs_e)
+    # the library's own graph cache still works afterwards on the same key
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eng.forward_fused(img, T, out=out, extrema=ext)
+        side.synchronize()
+    assert torch.equal(out[0], maps_e)
