@@ -6,7 +6,8 @@ C ABI in include/aaclip_b200.h).  Importing the package does not need a GPU; run
 """
 from .synth import ModelCfg, VIT_L_14_336  # noqa: F401
 
-__all__ = ["AdaptedCLIP", "CLIP", "create_model", "calculate_similarity_map", "Engine", "ModelCfg", "VIT_L_14_336"]
+__all__ = ["AdaptedCLIP", "CLIP", "create_model", "calculate_similarity_map", "Engine", "ModelCfg", "VIT_L_14_336",
+           "CLIPImageEncoder", "surgery_patch_features"]
 
 
 def __getattr__(name):
@@ -23,4 +24,7 @@ def __getattr__(name):
     if name == "Engine":
         from .engine import Engine
         return Engine
+    if name in ("CLIPImageEncoder", "surgery_patch_features"):
+        from . import surgery
+        return getattr(surgery, name)
     raise AttributeError(name)

@@ -19,7 +19,7 @@ INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libaaclip_b200.so"
 OBJ_DIR = PKG_DIR / "build"
 
-SOURCES = ["gemm_launch.cu", "attn.cu", "rowops.cu", "head.cu", "head_stream.cu", "preprocess.cu", "engine.cu"]
+SOURCES = ["gemm_launch.cu", "attn.cu", "vv_attn.cu", "rowops.cu", "head.cu", "head_stream.cu", "preprocess.cu", "engine.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

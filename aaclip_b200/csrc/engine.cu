@@ -113,6 +113,9 @@ struct aaclip_ctx {
   int cta_group = 0;   // 0: tile shape chosen per launch (k::launch_gemm); 1 / 2 / 3 force one
   // LayerNorm folded into the consumer GEMMs of the visual tower (see gemm_sm100.cuh); AACLIP_LN_FOLD=0 disables it
   bool ln_fold = true, fold_dirty = true;
+  // first block (0-based) of the visual tower whose attention is the batch-coupled v-v form of the surgery
+  // extractor (aaclip_dapm_replace; model/transformer.py:406-425); >= layers: none
+  int vv_first = INT_MAX;
   float2* part = nullptr;   // [rows][width / 128] (sum, sum of squares) per 128-column slice of the fp32 rows
   // CUDA graphs of the fused forward (aaclip_forward_fused), one per (batch, pointers, mode): the ~100 launches of a
   // chunk become one graph launch.  A key is run eagerly the first time, captured the second, replayed from then on.
@@ -234,7 +237,7 @@ int alloc_tower(aaclip_ctx* c, Tower& t, int n_adapters) {
 // One transformer block (+ optional adapter mix) over `rows` token rows of width t.width.
 // xn_ready: xn already holds ln_1(x) (written by the previous block's fused adapter mix).
 int run_block(aaclip_ctx* c, const Tower& t, int i, int B, int L, int causal, float adapt_w, bool* xn_ready,
-              cudaStream_t st) {
+              cudaStream_t st, bool vv = false) {
   const LayerW& l = t.lw[i];
   const int rows = B * L, w = t.width, ff = t.mlp;
   const int cg = c->cta_group;
@@ -243,9 +246,16 @@ int run_block(aaclip_ctx* c, const Tower& t, int i, int B, int L, int causal, fl
     RUN(PC_LAYERNORM, k::launch_layernorm(c->x, l.ln1_g, l.ln1_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st));
   }
   *xn_ready = false;
-  RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_w, w, rows, 3 * w, w, l.qkv_b, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
-                     nullptr, 0, cg, st));
-  RUN(PC_ATTENTION, k::launch_attention(c->qkv, c->att, B, L, t.heads, causal, st));
+  if (vv) {
+    // surgery block: only the value third of in_proj is needed (q and k feed the discarded `attn_ori`)
+    RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_w + 2LL * w * w, w, rows, w, w, l.qkv_b + 2 * w, c->qkv, w, gemm::ACT_NONE,
+                       gemm::OUT_BF16, nullptr, 0, cg, st));
+    RUN(PC_ATTENTION, k::launch_vv_attention(c->qkv, w, c->att, w, B, L, t.heads, st));
+  } else {
+    RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_w, w, rows, 3 * w, w, l.qkv_b, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
+                       nullptr, 0, cg, st));
+    RUN(PC_ATTENTION, k::launch_attention(c->qkv, c->att, B, L, t.heads, causal, st));
+  }
   RUN(PC_GEMM_OUT, k::launch_gemm(c->att, w, l.out_w, w, rows, w, w, l.out_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID,
                      nullptr, 0, cg, st));
   RUN(PC_LAYERNORM, k::launch_layernorm(c->x, l.ln2_g, l.ln2_b, eps, rows, w, 0, 0, 0, c->xn, nullptr, st));
@@ -294,10 +304,18 @@ int run_block_fold(aaclip_ctx* c, const Tower& t, int i, int B, int L, float ada
   cons.part_in = c->part; cons.slices = slices; cons.eps = 1e-5f;
   k::LnFold prod;
   prod.xb = c->xn; prod.ldxb = w; prod.part_out = c->part;
-  cons.colsum = l.qkv_cs;
-  RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_wf, w, rows, 3 * w, w, l.qkv_bf, c->qkv, 3 * w, gemm::ACT_NONE, gemm::OUT_BF16,
-                     nullptr, 0, cg, st, nullptr, nullptr, 0, &cons));
-  RUN(PC_ATTENTION, k::launch_attention(c->qkv, c->att, B, L, t.heads, 0, st));
+  if (i >= c->vv_first) {
+    // surgery block (model/transformer.py:123-152): value third of the folded in_proj, then the batch-coupled v-v attention
+    cons.colsum = l.qkv_cs + 2 * w;
+    RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_wf + 2LL * w * w, w, rows, w, w, l.qkv_bf + 2 * w, c->qkv, w, gemm::ACT_NONE,
+                       gemm::OUT_BF16, nullptr, 0, cg, st, nullptr, nullptr, 0, &cons));
+    RUN(PC_ATTENTION, k::launch_vv_attention(c->qkv, w, c->att, w, B, L, t.heads, st));
+  } else {
+    cons.colsum = l.qkv_cs;
+    RUN(PC_GEMM_QKV, k::launch_gemm(c->xn, w, l.qkv_wf, w, rows, 3 * w, w, l.qkv_bf, c->qkv, 3 * w, gemm::ACT_NONE,
+                       gemm::OUT_BF16, nullptr, 0, cg, st, nullptr, nullptr, 0, &cons));
+    RUN(PC_ATTENTION, k::launch_attention(c->qkv, c->att, B, L, t.heads, 0, st));
+  }
   RUN(PC_GEMM_OUT, k::launch_gemm(c->att, w, l.out_w, w, rows, w, w, l.out_b, c->x, w, gemm::ACT_NONE, gemm::OUT_F32_RESID_LN,
                      nullptr, 0, cg, st, nullptr, nullptr, 0, &prod));
   cons.colsum = l.fc_cs;
@@ -317,8 +335,12 @@ int run_block_fold(aaclip_ctx* c, const Tower& t, int i, int B, int L, float ada
 
 // seg_out[level] (fp32 [B,P,E], optional), det_out (fp32 [B,E], optional), dots (optional, [levels][B*P][2] with
 // anchors) for one chunk of B <= max_batch images.
+// raw_out[level] (fp32 [B,L,width], optional): the residual stream after block levels[level] (Transformer.forward's
+// out_tokens, model/transformer.py:296-318); pooled_out (fp32 [B,E], optional): ln_post(class token) @ proj, L2-normalised
+// when pooled_normalize (VisionTransformer.forward :542-546, CLIP.encode_image model/model.py:185-188).
 int visual_chunk(aaclip_ctx* c, const float* image, int B, void* const* seg_out, int seg_is_bf16, long long seg_off,
-                 float* det_out, const float* anchors, float* dots, cudaStream_t st) {
+                 float* det_out, const float* anchors, float* dots, cudaStream_t st, float* const* raw_out = nullptr,
+                 long long raw_off = 0, float* pooled_out = nullptr, int pooled_normalize = 0) {
   const aaclip_cfg& cfg = c->cfg;
   const int w = cfg.width, L = c->L, P = c->P, E = c->E, rows = B * L, prow = B * P;
   const int cg = c->cta_group;
@@ -340,17 +362,21 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, void* const* seg_out,
   int level = 0;
   for (int i = 0; i < cfg.layers; ++i) {
     if (fold) TRY(run_block_fold(c, c->v, i, B, L, cfg.image_adapt_weight, st));
-    else TRY(run_block(c, c->v, i, B, L, 0, cfg.image_adapt_weight, &xn_ready, st));
+    else TRY(run_block(c, c->v, i, B, L, 0, cfg.image_adapt_weight, &xn_ready, st, i >= c->vv_first));
     if (level < cfg.n_levels && cfg.levels[level] == i + 1) {
       const bool last = (level == cfg.n_levels - 1);
-      // tap: x[:, 1:, :] -> ln_post -> seg_proj (and det_proj on the last tap)   (model/adapter.py:100-111)
-      RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_post_g, c->ln_post_b, 1e-5f, prow, w, P, 1, (long long)L * w, c->tap,
-                              nullptr, st));
+      if (raw_out && raw_out[level])
+        AACLIP_CUDA_CHECK(cudaMemcpyAsync(raw_out[level] + raw_off, c->x, (size_t)rows * w * sizeof(float),
+                                          cudaMemcpyDeviceToDevice, st));
       const bool want_det = last && (det_out != nullptr);
       const int n_out = want_det ? 2 * E : E;
       // seg tokens leave as fp32 (the reference's dtype) or bf16 (half the bytes for the head to stream)
       void* so = (seg_out && seg_out[level])
                      ? static_cast<void*>(static_cast<uint8_t*>(seg_out[level]) + seg_off * (seg_is_bf16 ? 2 : 4)) : nullptr;
+      if (!so && !dots && !want_det) { ++level; continue; }   // encode_image: nothing is projected at this level
+      // tap: x[:, 1:, :] -> ln_post -> seg_proj (and det_proj on the last tap)   (model/adapter.py:100-111)
+      RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_post_g, c->ln_post_b, 1e-5f, prow, w, P, 1, (long long)L * w, c->tap,
+                              nullptr, st));
       const int act = cfg.proj_relu ? gemm::ACT_LEAKY : gemm::ACT_NONE;
       if (dots && !so && E % 128 == 0) {
         // fused path: the normalised seg tokens are never materialised - the GEMM epilogue leaves the partial sums
@@ -374,11 +400,36 @@ int visual_chunk(aaclip_ctx* c, const float* image, int B, void* const* seg_out,
   if (dots && !seg_out && E % 128 == 0) {
     RUN(PC_L2NORM, k::launch_dots_finish(c->partials, cfg.n_levels, prow, E / 128, dots, st));
   }
+  if (pooled_out) {
+    // pooled = ln_post(x[:, 0]) @ proj: the class token of every image through the projection the last seg_proj slot
+    // holds (a context built for CLIP.encode_image carries visual.proj^T there)
+    RUN(PC_LAYERNORM, k::launch_layernorm(c->x, c->ln_post_g, c->ln_post_b, 1e-5f, B, w, 1, 0, (long long)L * w, c->tap, nullptr,
+                                          st));
+    RUN(PC_GEMM_SEGDET, k::launch_gemm(c->tap, w, c->segdet_w[cfg.n_levels - 1], w, B, E, w, nullptr, c->s, 2 * E, gemm::ACT_NONE,
+                                       gemm::OUT_F32, nullptr, 0, cg, st));
+    if (pooled_normalize) {
+      RUN(PC_L2NORM, k::launch_l2norm_rows(c->s, 2 * E, 0, B, E, pooled_out, nullptr, nullptr, nullptr, st));
+    } else {
+      AACLIP_CUDA_CHECK(cudaMemcpy2DAsync(pooled_out, (size_t)E * sizeof(float), c->s, (size_t)2 * E * sizeof(float),
+                                          (size_t)E * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    }
+  }
   return host::OK;
 }
 
 int check_ready(const aaclip_ctx* c) {
   if (!c) return host::fail(host::ERR_INVALID, "null context");
+  return host::OK;
+}
+
+// The v-v attention couples the images of a batch (vv_attn.cu): such a context never splits a batch into chunks.
+int check_vv_batch(const aaclip_ctx* c, int B, const char* who) {
+  if (c->vv_first >= c->cfg.layers) return host::OK;
+  const int cap = std::min(c->cfg.max_batch, k::vv_attention_max_batch());
+  if (B > cap)
+    return host::fail(host::ERR_INVALID, "%s: batch %d on a context with v-v (surgery) attention, which couples the images "
+                                         "of a batch: at most min(max_batch, %d) = %d images per call", who, B,
+                      k::vv_attention_max_batch(), cap);
   return host::OK;
 }
 
@@ -632,6 +683,7 @@ extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, v
                                      float* det_out, void* stream_) {
   TRY(check_ready(c));
   if (B < 0 || (B > 0 && !image)) return host::fail(host::ERR_INVALID, "visual_forward: B=%d image=%p", B, (const void*)image);
+  TRY(check_vv_batch(c, B, "visual_forward"));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   ENTER_DEVICE(c);
   const long long img_elems = 3LL * c->cfg.image_size * c->cfg.image_size;
@@ -639,6 +691,47 @@ extern "C" int aaclip_visual_forward(aaclip_ctx* c, const float* image, int B, v
     const int nb = std::min(c->cfg.max_batch, B - b0);
     TRY(visual_chunk(c, image + b0 * img_elems, nb, seg_out, seg_is_bf16 != 0, (long long)b0 * c->P * c->E,
                      det_out ? det_out + (long long)b0 * c->E : nullptr, nullptr, nullptr, st));
+  }
+  return host::OK;
+}
+
+// VisionTransformer.DAPM_replace(DPAM_layer) (model/transformer.py:406-425; train.py:243): the last DPAM_layer - 1
+// blocks of the visual tower use the v-v `Attention` (transformer.py:123-152) with the block's own in_proj / out_proj
+// weights.  dpam_layer <= 1 restores the ordinary attention everywhere.
+extern "C" int aaclip_dapm_replace(aaclip_ctx* c, int dpam_layer) {
+  TRY(check_ready(c));
+  const int n = dpam_layer > 1 ? dpam_layer - 1 : 0;
+  if (n > c->cfg.layers)
+    return host::fail(host::ERR_INVALID, "dapm_replace: DPAM_layer %d reaches past the %d blocks of the visual tower",
+                      dpam_layer, c->cfg.layers);
+  const int first = n > 0 ? c->cfg.layers - n : INT_MAX;
+  if (first == c->vv_first) return host::OK;
+  ENTER_DEVICE(c);
+  // graphs captured with the other attention are stale
+  AACLIP_CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
+  c->seen_once.clear();
+  c->vv_first = first;
+  return host::OK;
+}
+
+// CLIP.encode_image(image, out_layers, normalize) (model/model.py:185-188) = VisionTransformer.forward
+// (model/transformer.py:490-551): tokens_out[i] fp32 [B, L, width] = the residual stream after block cfg.levels[i]
+// (class token first), pooled_out fp32 [B, E] = ln_post(class token) @ proj.  Either may be null.  The context's levels
+// are the out_layers; its seg_proj slots hold visual.proj^T (see aaclip_b200/surgery.py).
+extern "C" int aaclip_encode_image(aaclip_ctx* c, const float* image, int B, float* const* tokens_out, float* pooled_out,
+                                   int normalize, void* stream_) {
+  TRY(check_ready(c));
+  if (B < 0 || (B > 0 && !image)) return host::fail(host::ERR_INVALID, "encode_image: B=%d image=%p", B, (const void*)image);
+  TRY(check_vv_batch(c, B, "encode_image"));
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  ENTER_DEVICE(c);
+  const long long img_elems = 3LL * c->cfg.image_size * c->cfg.image_size;
+  for (int b0 = 0; b0 < B; b0 += c->cfg.max_batch) {
+    const int nb = std::min(c->cfg.max_batch, B - b0);
+    TRY(visual_chunk(c, image + b0 * img_elems, nb, nullptr, 0, 0, nullptr, nullptr, nullptr, st, tokens_out,
+                     (long long)b0 * c->L * c->cfg.width, pooled_out ? pooled_out + (long long)b0 * c->E : nullptr, normalize));
   }
   return host::OK;
 }
@@ -737,6 +830,7 @@ extern "C" int aaclip_forward_fused(aaclip_ctx* c, const float* image, int B, co
   if (mode != AACLIP_HEAD_TEST_INDUSTRIAL && mode != AACLIP_HEAD_TEST_MEDICAL)
     return host::fail(host::ERR_INVALID, "forward_fused: only the test modes are fused (mode=%d)", mode);
   if (minmax_out && !maps_out) return host::fail(host::ERR_INVALID, "forward_fused: extrema are produced with the maps");
+  TRY(check_vv_batch(c, B, "forward_fused"));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   ENTER_DEVICE(c);
   const int S = c->cfg.image_size;
@@ -860,6 +954,7 @@ extern "C" int aaclip_forward_fused_host(aaclip_ctx* c, const float* host_image,
                                          int mode, float* host_maps_out, float* host_scores_out, float* host_minmax_out) {
   TRY(check_ready(c));
   if (B <= 0) return host::OK;
+  TRY(check_vv_batch(c, B, "forward_fused_host"));
   for (const auto& sl : c->slots)
     if (sl.busy) return host::fail(host::ERR_STATE, "forward_fused_host: ticket %lld is still pending", sl.ticket);
   const int S = c->cfg.image_size, mb = c->cfg.max_batch;

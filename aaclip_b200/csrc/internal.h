@@ -69,6 +69,15 @@ int launch_cls_rows(float* x, const float* cls, const float* pos, int B, int L, 
 // out bf16 [M, width].  causal: additive -inf above the diagonal (text tower).  scale = 1/sqrt(64).
 int launch_attention(const void* qkv, void* out, int B, int L, int heads, int causal, cudaStream_t stream);
 
+// v-v attention of the surgery feature extractor (model/transformer.py:123-152 as installed by DAPM_replace :406-425):
+// v bf16 [B*L, ldv] (value projection, heads contiguous 64-wide), out bf16 [B*L, ldo]; for every (token, head) the
+// B images of the batch attend to each other: softmax(v v^T / 8) v.  B <= vv_attention_max_batch().  See vv_attn.cu.
+int launch_vv_attention(const void* v, int ldv, void* out, int ldo, int B, int L, int heads, cudaStream_t stream);
+int vv_attention_max_batch();
+
+// tokens[b, p, :] += vec[b, :]   (train.py:85: patch features + the image's class feature)
+int launch_add_image_vector(float* tokens, const float* vec, int B, int P, int E, cudaStream_t stream);
+
 // Anomaly-map head (forward_utils.py:196-216 + test.py:83-93), see head.cu
 int launch_patch_dots(const void* const* seg, int n_levels, int seg_is_bf16, const float* anchors, int anchors_batched,
                       int B, int P, int E, float* dots /*[n_levels][B*P][2]*/, cudaStream_t stream);

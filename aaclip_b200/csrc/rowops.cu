@@ -382,6 +382,21 @@ inline int row_blocks(int rows) { return (rows + WARPS_PER_BLOCK - 1) / WARPS_PE
     default: return host::fail(host::ERR_INVALID, "row kernel: unsupported width %d", (width)); \
   }
 
+// tokens[b, p, :] += vec[b, :]   (train.py:85: `t + cls_token.unsqueeze(1)`); float4 lanes, E % 4 == 0
+__global__ void add_image_vector_kernel(float* __restrict__ tokens, const float* __restrict__ vec, int P, int E4,
+                                        long long total4) {
+  ptx::grid_dep_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % E4);
+    const long long b = i / ((long long)P * E4);
+    float4 t = reinterpret_cast<float4*>(tokens)[i];
+    const float4 a = reinterpret_cast<const float4*>(vec)[b * E4 + c];
+    t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    reinterpret_cast<float4*>(tokens)[i] = t;
+  }
+}
+
 }  // namespace
 
 int k::launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int rows, int width,
@@ -466,6 +481,16 @@ int k::launch_det_mean(const float* s, int ld, int col0, int B, int P, int width
   return host::OK;
 }
 
+int k::launch_add_image_vector(float* tokens, const float* vec, int B, int P, int E, cudaStream_t stream) {
+  const long long total4 = (long long)B * P * E / 4;
+  if (total4 <= 0) return host::OK;
+  if (E % 4 != 0 || (reinterpret_cast<uintptr_t>(tokens) & 15u) != 0 || (reinterpret_cast<uintptr_t>(vec) & 15u) != 0)
+    return host::fail(host::ERR_INVALID, "add_image_vector: E %d and the pointers must be 16-byte aligned", E);
+  const unsigned grid = (unsigned)std::min<long long>((total4 + 255) / 256, 148 * 16);
+  AACLIP_CUDA_CHECK(host::launch(add_image_vector_kernel, dim3(grid), dim3(256), 0, stream, tokens, vec, P, E / 4, total4));
+  return host::OK;
+}
+
 int k::launch_dots_finish(const void* partials, int n_levels, int rows, int n_slices, float* dots, cudaStream_t stream) {
   const long long total = (long long)n_levels * rows;
   if (total <= 0) return host::OK;
@@ -524,4 +549,11 @@ extern "C" int aaclip_fold_ln_weight(const float* W, const float* bias, const fl
   host::PointerDeviceGuard dev_guard(W);
   if (!W || !gamma || !beta || !Wf || !colsum || !bias_f) return host::fail(host::ERR_INVALID, "fold_ln_weight: null argument");
   return k::launch_fold_ln_weight(W, bias, gamma, beta, N, K, Wf, colsum, bias_f, static_cast<cudaStream_t>(stream));
+}
+
+// tokens fp32 [B, P, E] += vec fp32 [B, E] broadcast over the patches (train.py:85)
+extern "C" int aaclip_add_image_vector(float* tokens, const float* vec, int B, int P, int E, void* stream) {
+  if (B > 0 && (!tokens || !vec)) return host::fail(host::ERR_INVALID, "add_image_vector: null argument");
+  host::PointerDeviceGuard dev_guard(tokens);
+  return k::launch_add_image_vector(tokens, vec, B, P, E, static_cast<cudaStream_t>(stream));
 }

@@ -173,6 +173,26 @@ class Engine:
                                              self._stream()))
         return seg, det
 
+    def dapm_replace(self, dpam_layer: Optional[int]) -> None:
+        """VisionTransformer.DAPM_replace(DPAM_layer) (model/transformer.py:406-425): the last DPAM_layer - 1 visual
+        blocks use the batch-coupled v-v attention (:123-152).  None / 0 / 1 restores ordinary attention."""
+        check(self.lib.aaclip_dapm_replace(self._ctx, int(dpam_layer or 0)))
+
+    def encode_image(self, image: torch.Tensor, want_tokens: bool = True, want_pooled: bool = True,
+                     normalize: bool = False):
+        """CLIP.encode_image(image, cfg.levels, normalize) (model/model.py:185-188): returns (pooled fp32 [B,E] or
+        None, list of fp32 [B,L,width] residual-stream tokens after each block in cfg.levels).  The context must have
+        been loaded with visual.proj^T in its seg_proj slots (aaclip_b200.surgery.CLIPImageEncoder does that)."""
+        self._check_image(image)
+        B = image.shape[0]
+        cfg = self.cfg
+        toks = [torch.empty(B, cfg.tokens, cfg.width, device=image.device, dtype=torch.float32)
+                for _ in cfg.levels] if want_tokens else []
+        pooled = torch.empty(B, cfg.embed_dim, device=image.device, dtype=torch.float32) if want_pooled else None
+        arr = (C.c_void_p * len(cfg.levels))(*[t.data_ptr() for t in toks]) if want_tokens else None
+        check(self.lib.aaclip_encode_image(self._ctx, ptr(image), B, arr, ptr(pooled), int(normalize), self._stream()))
+        return pooled, toks
+
     def forward_fused(self, image: torch.Tensor, anchors: torch.Tensor, domain: str = "Industrial",
                       want_maps: bool = True, want_scores: bool = True, out=None, extrema: Optional[torch.Tensor] = None):
         """image -> (level-summed anomaly maps fp32 [B,S,S], image scores fp32 [B]) without seg tokens.

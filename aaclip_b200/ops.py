@@ -218,3 +218,25 @@ def gemm_lnfold(xb: torch.Tensor, wf: torch.Tensor, bias_f: torch.Tensor, colsum
     check(_lib.load().aaclip_gemm_lnfold(ptr(xb), K, ptr(wf), K, M, N, K, ptr(bias_f), ptr(colsum), ptr(part),
                                          part.shape[1], eps, ptr(out), N, act, cta_group, cur_stream(xb.device)))
     return out
+
+
+def vv_attention(v: torch.Tensor, B: int, L: int, heads: int) -> torch.Tensor:
+    """The surgery extractor's v-v attention (model/transformer.py:123-152 under DAPM_replace): v bf16 [B*L, heads*64]
+    (row = b*L + l) -> bf16 [B*L, heads*64]; for every (token l, head) the B images attend to each other:
+    out[b] = sum_b' softmax_b'(<v[b], v[b']> / 8) v[b'].  Batch-coupled by construction; B <= 128."""
+    _need(v, torch.bfloat16, "v")
+    if v.dim() != 2 or v.shape[0] != B * L or v.shape[1] != heads * 64:
+        raise ValueError(f"v shape {tuple(v.shape)} != ({B * L}, {heads * 64})")
+    out = torch.empty(B * L, heads * 64, device=v.device, dtype=torch.bfloat16)
+    check(_lib.load().aaclip_vv_attention(ptr(v), v.stride(0), ptr(out), heads * 64, B, L, heads, cur_stream(v.device)))
+    return out
+
+
+def add_image_vector(tokens: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
+    """In place: tokens fp32 [B, P, E] += vec fp32 [B, E] broadcast over the patches (train.py:85)."""
+    _need(tokens, torch.float32, "tokens"); _need(vec, torch.float32, "vec")
+    B, P, E = tokens.shape
+    if tuple(vec.shape) != (B, E):
+        raise ValueError(f"vec shape {tuple(vec.shape)} != ({B}, {E})")
+    check(_lib.load().aaclip_add_image_vector(ptr(tokens), ptr(vec), B, P, E, cur_stream(tokens.device)))
+    return tokens

@@ -212,6 +212,29 @@ int aaclip_submit_host_u8(aaclip_ctx* ctx, const uint8_t* host_u8, int B, int H0
                           int mode, float* host_maps_out, float* host_scores_out, float* host_minmax_out,
                           long long* ticket);
 
+/* ---- stage-1 feature extraction of train.py (forward only, runs under no_grad) ------------ */
+/* VisionTransformer.DAPM_replace(DPAM_layer) (model/transformer.py:406-425; train.py:243, default 20): the last
+ * DPAM_layer - 1 blocks of the visual tower switch to the v-v `Attention` (model/transformer.py:123-152) with their
+ * own in_proj / out_proj weights; DPAM_layer <= 1 switches back.  That attention reads the block's [L, batch, D]
+ * tensor as (B, N, C), so its softmax runs over the IMAGES OF THE BATCH for every token position and head: results
+ * depend on the batch composition, and such a context refuses batches it would have to split
+ * (B > min(max_batch, 128)).  Graphs cached by the fused forward are dropped. */
+int aaclip_dapm_replace(aaclip_ctx* ctx, int dpam_layer);
+/* CLIP.encode_image(image, out_layers, normalize) (model/model.py:185-188) = VisionTransformer.forward
+ * (model/transformer.py:490-551) on a context whose cfg.levels are the out_layers, whose adapters are off
+ * (image_adapt_until = 0) and whose seg_proj slots hold visual.proj^T:
+ *   tokens_out[i]  fp32 [B, L, width] or NULL: residual stream after block levels[i], class token first
+ *                  (Transformer.forward out_tokens, model/transformer.py:296-318); tokens_out itself may be NULL
+ *   pooled_out     fp32 [B, E] or NULL: ln_post(class token) @ proj, L2-normalised when normalize != 0.
+ * On such a context aaclip_visual_forward returns normalize(ln_post(tokens[:, 1:]) @ proj) per level: train.py:78-84. */
+int aaclip_encode_image(aaclip_ctx* ctx, const float* image, int B, float* const* tokens_out, float* pooled_out,
+                        int normalize, void* stream);
+/* The v-v attention alone: v bf16 [B*L, ldv] (value projection in columns [0, heads*64)), out bf16 [B*L, ldo];
+ * out[b, l, h] = sum_b' softmax_b'(<v[b,l,h], v[b',l,h]> / 8) v[b',l,h].  B <= 128. */
+int aaclip_vv_attention(const void* v, int ldv, void* out, int ldo, int B, int L, int heads, void* stream);
+/* tokens fp32 [B, P, E] += vec fp32 [B, E] broadcast over the P patches (train.py:85, `t + cls_token.unsqueeze(1)`). */
+int aaclip_add_image_vector(float* tokens, const float* vec, int B, int P, int E, void* stream);
+
 /* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
 /* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */
 int aaclip_text_forward(aaclip_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);

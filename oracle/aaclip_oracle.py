@@ -109,6 +109,70 @@ def visual_forward(clip_sd: SD, image_adapter_sd: SD, image: torch.Tensor, *, pa
     return seg, det
 
 
+# ----------------------------------------------------------------------------------------------- surgery (train.py stage 1)
+def vv_attention(x: torch.Tensor, sd: SD, prefix: str, heads: int) -> torch.Tensor:
+    """`Attention.forward` (model/transformer.py:123-152) as installed by `DAPM_replace` (:406-425) and called from
+    `ResidualAttentionBlock.attention` (:226-237) with the block's [L, batch, D] tensor.  The module reads the shape
+    as (B, N, C) = (L, batch, D): its softmax therefore runs over the IMAGES OF THE BATCH for every token position
+    and head.  q and k only feed `attn_ori` / `x_ori`, which are discarded (:133-136, :147, :150); the returned x is
+    proj(softmax(v v^T * scale) v).  x here is [batch, L, D] (batch-first restatement); returns [batch, L, D]."""
+    B, L, D = x.shape
+    hd = D // heads
+    qkv = F.linear(x, sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"])     # self.qkv(q_x), weights :412-417
+    v = qkv[..., 2 * D:].reshape(B, L, heads, hd).permute(1, 2, 0, 3)                  # [L, heads, batch, hd]
+    attn = torch.softmax((v @ v.transpose(-2, -1)) * hd ** -0.5, dim=-1)              # :142-145, [L, heads, batch, batch]
+    o = (attn @ v).permute(2, 0, 1, 3).reshape(B, L, D)                                # :148
+    return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])  # :149, weights :418-423
+
+
+def encode_image(clip_sd: SD, image: torch.Tensor, out_layers: Sequence[int], *, patch_size: int = 14, heads: int = 16,
+                 layers: int = 24, surgery_until_layer: Optional[int] = None, quick_gelu: bool = False,
+                 normalize: bool = False):
+    """`CLIP.encode_image(image, out_layers, normalize)` (model/model.py:185-188) -> `VisionTransformer.forward`
+    (model/transformer.py:490-551) -> `Transformer.forward` (:296-318).  `surgery_until_layer` = the DPAM_layer given
+    to `DAPM_replace` (:406-425; train.py:243): blocks[-i] for i in 1..DPAM_layer-1 use `vv_attention`.
+    Returns (pooled [B, E], [tokens [B, L, D] after each block in out_layers])."""
+    sd = clip_sd
+    x = F.conv2d(image, sd["visual.conv1.weight"], stride=patch_size)          # :507-509
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+    cls = sd["visual.class_embedding"] + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype, device=x.device)
+    x = torch.cat([cls, x], dim=1)                                             # :512-521
+    x = x + sd["visual.positional_embedding"]                                  # :522
+    x = layer_norm(x, sd, "visual.ln_pre.")                                    # :525-526 (patch_dropout: identity in eval)
+    n_vv = max(int(surgery_until_layer) - 1, 0) if surgery_until_layer is not None else 0
+    tokens = []
+    for i in range(layers):                                                    # Transformer.forward :304-316
+        prefix = f"visual.transformer.resblocks.{i}."
+        if i >= layers - n_vv:
+            # ResidualAttentionBlock.forward :239-258 with self.attn = Attention
+            x = x + vv_attention(layer_norm(x, sd, prefix + "ln_1."), sd, prefix + "attn.", heads)
+            h = F.linear(layer_norm(x, sd, prefix + "ln_2."), sd[prefix + "mlp.c_fc.weight"], sd[prefix + "mlp.c_fc.bias"])
+            x = x + F.linear(activation(h, quick_gelu), sd[prefix + "mlp.c_proj.weight"], sd[prefix + "mlp.c_proj.bias"])
+        else:
+            x = residual_attention_block(x, sd, prefix, heads, quick_gelu, None)
+        if i + 1 in out_layers:
+            tokens.append(x)
+    pooled = layer_norm(x[:, 0], sd, "visual.ln_post.") @ sd["visual.proj"]    # :542-546 (_global_pool :484-488: class token)
+    if normalize:
+        pooled = F.normalize(pooled, dim=-1)
+    return pooled, tokens
+
+
+def surgery_patch_features(surgery_sd: SD, clip_sd: SD, image: torch.Tensor, *, levels: Sequence[int] = (6, 12, 18, 24),
+                           surgery_until_layer: int = 20, patch_size: int = 14, heads: int = 16, layers: int = 24,
+                           quick_gelu: bool = False) -> List[torch.Tensor]:
+    """train.py:74-85, the frozen stage-1 feature extractor: patch tokens of the surgery CLIP at `levels` -> ln_post ->
+    @ visual.proj -> / norm, plus the (normalised) pooled class feature of the unmodified CLIP.  -> list of [B, P, E]."""
+    kw = dict(patch_size=patch_size, heads=heads, layers=layers, quick_gelu=quick_gelu)
+    _, toks = encode_image(surgery_sd, image, levels, surgery_until_layer=surgery_until_layer, **kw)     # :75
+    cls, _ = encode_image(clip_sd, image, [], **kw)                                                      # :76
+    cls = cls / cls.norm(dim=-1, keepdim=True)                                                           # :77
+    feats = [layer_norm(t[:, 1:, :], surgery_sd, "visual.ln_post.") for t in toks]                       # :78-80
+    feats = [t @ surgery_sd["visual.proj"] for t in feats]                                               # :81
+    feats = [t / t.norm(dim=-1, keepdim=True) for t in feats]                                            # :82-84
+    return [t + cls.unsqueeze(1) for t in feats]                                                         # :85
+
+
 # ----------------------------------------------------------------------------------------------- text
 def causal_mask(n: int) -> torch.Tensor:
     """CLIP.attn_mask (model/model.py:172; build_attention_mask transformer.py:629-635)."""

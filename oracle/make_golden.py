@@ -211,6 +211,41 @@ def main():
                 "visual.positional_embedding": ref_sd["visual.positional_embedding"].clone()},
                os.path.join(out_dir, "openai_ingest_tiny.pt"))
 
+    # ---- stage-1 feature extraction of train.py:74-85: the surgery CLIP (DAPM_replace, v-v attention
+    #      over the batch for the last 19 blocks) + the class feature of the unmodified CLIP.  B = 3 so that the batch
+    #      coupling is exercised with an odd batch.
+    import copy
+    Bs = 3
+    img_s = synth.images(Bs, cfg, seed=4)
+    levels = [6, 12, 18, 24]
+    clip_plain = model.clipmodel
+    clip_surgery = copy.deepcopy(clip_plain).eval()
+    clip_surgery.visual.DAPM_replace(DPAM_layer=20)                                         # train.py:243
+    with torch.no_grad():
+        pooled_s, toks_s = clip_surgery.encode_image(img_s, levels)                          # train.py:75
+        cls_token, _ = clip_plain.encode_image(img_s, [])                                    # :76
+        cls_n = cls_token / cls_token.norm(dim=-1, keepdim=True)                             # :77
+        feats = [clip_surgery.visual.ln_post(t[:, 1:, :]) for t in toks_s]                   # :78-80
+        feats = [t @ clip_surgery.visual.proj for t in feats]                                # :81
+        feats = [t / t.norm(dim=-1, keepdim=True) for t in feats]                            # :82-84
+        feats = [t + cls_n.unsqueeze(1) for t in feats]                                      # :85
+        pooled_o, toks_o = orc.encode_image(sd, img_s, levels, surgery_until_layer=20)
+        cls_o, _ = orc.encode_image(sd, img_s, [])
+        feats_o = orc.surgery_patch_features(sd, sd, img_s, levels=levels, surgery_until_layer=20)
+    report["surgery_tokens_rel_maxdiff"] = max(maxdiff(a, b) / float(a.abs().max()) for a, b in zip(toks_s, toks_o))
+    report["surgery_pooled_maxdiff"] = maxdiff(pooled_s, pooled_o) / float(pooled_s.abs().max())
+    report["plain_pooled_maxdiff"] = maxdiff(cls_token, cls_o) / float(cls_token.abs().max())
+    report["surgery_features_maxdiff"] = max(maxdiff(a, b) for a, b in zip(feats, feats_o))
+    tok_idx = torch.arange(0, cfg.tokens, 41)
+    torch.save({
+        "cfg": "ViT-L-14-336", "seed": seed, "image_seed": 4, "batch": Bs, "levels": levels, "surgery_until_layer": 20,
+        "patch_idx": patch_idx, "token_idx": tok_idx,
+        "features_sub": [f[:, patch_idx].clone() for f in feats],         # 4 x [3,16,768]  (train.py:85)
+        "tokens_sub": [t[:, tok_idx].clone() for t in toks_s],            # 4 x [3,15,1024] (encode_image out_tokens)
+        "pooled_surgery": pooled_s.clone(),                               # [3,768]
+        "pooled_plain": cls_token.clone(),                                # [3,768]
+    }, os.path.join(out_dir, "surgery_vitl336_b3.pt"))
+
     json.dump(report, open(os.path.join(out_dir, "oracle_vs_reference.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(report, indent=1, sort_keys=True))
     bad = {k: v for k, v in report.items() if not v < 2e-4}

@@ -326,3 +326,61 @@ def test_container_block_forward_raises_clearly():
     blk = CLIP(synth.tiny_cfg(), text=False).visual.transformer.resblocks[0]
     with pytest.raises(NotImplementedError, match="CUDA engine"):
         blk(torch.zeros(5, 1, 256))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "model")), reason="the reference tree is not on this machine")
+def test_dapm_replaced_reference_clip_maps_onto_the_surgery_encoder():
+    """(f)4 guard: a REAL reference CLIP whose visual tower went through DAPM_replace(20) (train.py:243) carries
+    `attn.qkv` / `attn.proj` Linears in its last 19 blocks.  CLIPImageEncoder reads the surgery depth off those keys, and
+    every visual tensor the engine wants is found under its canonical (nn.MultiheadAttention) name with the same shape."""
+    import importlib
+    import json
+    import types
+    for name in ("ipdb", "ftfy"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["ftfy"].fix_text = getattr(sys.modules["ftfy"], "fix_text", lambda t: t)
+    sys.path.insert(0, REFERENCE)
+    try:
+        from model.model import CLIP as RefCLIP
+        jcfg = json.load(open(os.path.join(REFERENCE, "model/model_configs/ViT-L-14-336.json")))
+        with torch.device("meta"):
+            ref_clip = RefCLIP(**jcfg)
+            ref_clip.visual.DAPM_replace(DPAM_layer=20)
+        from aaclip_b200.adapter import _infer_cfg
+        from aaclip_b200.engine import weight_map
+        from aaclip_b200.surgery import CLIPImageEncoder, _canonical_key
+        enc = CLIPImageEncoder(ref_clip, [6, 12, 18, 24])
+        assert enc.surgery_until_layer == 20
+        keys = list(ref_clip.state_dict().keys())
+        assert "visual.transformer.resblocks.5.attn.qkv.weight" in keys          # first replaced block (0-based 5)
+        assert "visual.transformer.resblocks.4.attn.in_proj_weight" in keys      # last ordinary one
+        canon = {"clip." + _canonical_key(k): v for k, v in ref_clip.state_dict().items()}
+        cfg = _infer_cfg(ref_clip, [6, 12, 18, 24], 0, 0, 0.0, 0.0, False)
+        assert (cfg.width, cfg.layers, cfg.heads, cfg.image_size) == (1024, 24, 16, 336)
+        wm = weight_map(cfg, text=False)
+        missing = [k for k in wm if k.startswith("clip.visual.") and k not in canon]
+        assert not missing, missing[:5]
+        assert tuple(canon["clip.visual.transformer.resblocks.23.attn.in_proj_weight"].shape) == (3072, 1024)
+        assert tuple(canon["clip.visual.transformer.resblocks.23.attn.out_proj.bias"].shape) == (1024,)
+        assert tuple(canon["clip.visual.proj"].shape) == (1024, 768)
+        # an untouched CLIP is not mistaken for a surgery model
+        with torch.device("meta"):
+            plain = RefCLIP(**jcfg)
+        assert CLIPImageEncoder(plain, []).surgery_until_layer is None
+    finally:
+        sys.path.remove(REFERENCE)
+        for m in [m for m in sys.modules if m == "model" or m.startswith("model.")]:
+            del sys.modules[m]
+
+
+def test_surgery_encoder_refuses_cpu_inputs():
+    from aaclip_b200.clip import CLIP
+    from aaclip_b200.surgery import CLIPImageEncoder
+    enc = CLIPImageEncoder(CLIP(synth.tiny_cfg(), text=False), [2, 4], surgery_until_layer=3)
+    with pytest.raises(RuntimeError, match="B200 only"):
+        enc.encode_image(torch.zeros(1, 3, 56, 56))
+    with pytest.raises(RuntimeError, match="B200 only"):
+        enc.patch_features(torch.zeros(1, 3, 56, 56))

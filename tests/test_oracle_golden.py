@@ -102,3 +102,38 @@ def test_gaussian_blur_against_independent_implementation():
         want = np.stack([ndi.gaussian_filter(x[i, 0].numpy().astype(np.float64), sigma=s, radius=k // 2, mode="mirror")
                          for i in range(3)])[:, None]
         assert np.abs(got - want).max() < 2e-6
+
+
+def test_surgery_feature_extractor_vs_reference_golden(weights):
+    """train.py:74-85 with DAPM_replace(20) on the real reference CLIP (oracle/make_golden.py) vs the restatement."""
+    cfg, sd, _, _ = weights
+    g = _load("surgery_vitl336_b3.pt")
+    img = synth.images(g["batch"], cfg, seed=g["image_seed"])
+    with torch.no_grad():
+        pooled, toks = orc.encode_image(sd, img, g["levels"], surgery_until_layer=g["surgery_until_layer"])
+        pooled_plain, none = orc.encode_image(sd, img, [])
+        feats = orc.surgery_patch_features(sd, sd, img, levels=g["levels"], surgery_until_layer=g["surgery_until_layer"])
+    assert none == []
+    for t, ref in zip(toks, g["tokens_sub"]):
+        assert (t[:, g["token_idx"]] - ref).abs().max() < TOL * ref.abs().max()
+    assert (pooled - g["pooled_surgery"]).abs().max() < TOL * g["pooled_surgery"].abs().max()
+    assert (pooled_plain - g["pooled_plain"]).abs().max() < TOL * g["pooled_plain"].abs().max()
+    for f, ref in zip(feats, g["features_sub"]):
+        assert (f[:, g["patch_idx"]] - ref).abs().max() < TOL
+
+
+def test_vv_attention_properties():
+    """The restated `Attention.forward` (model/transformer.py:123-152): one image -> the out-projected value itself;
+    the images of a batch are coupled; permuting the batch permutes the result."""
+    torch.manual_seed(0)
+    D, heads, L = 128, 2, 5
+    sd = {"a.in_proj_weight": torch.randn(3 * D, D) * D ** -0.5, "a.in_proj_bias": torch.randn(3 * D) * 0.1,
+          "a.out_proj.weight": torch.randn(D, D) * D ** -0.5, "a.out_proj.bias": torch.randn(D) * 0.1}
+    x = torch.randn(4, L, D)
+    out = orc.vv_attention(x, sd, "a.", heads)
+    v1 = torch.nn.functional.linear(x[:1], sd["a.in_proj_weight"], sd["a.in_proj_bias"])[..., 2 * D:]
+    one = orc.vv_attention(x[:1], sd, "a.", heads)
+    assert torch.allclose(one, torch.nn.functional.linear(v1, sd["a.out_proj.weight"], sd["a.out_proj.bias"]), atol=1e-5)
+    assert (out[:1] - one).abs().max() > 1e-3
+    perm = torch.tensor([2, 0, 3, 1])
+    assert torch.allclose(orc.vv_attention(x[perm], sd, "a.", heads), out[perm], atol=1e-5)
