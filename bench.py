@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-drop-in", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="append the batch sweep 1..2048 (BASELINE.json configs[4])")
     ap.add_argument("--text", action="store_true", help="append the text-anchor path (BASELINE.json configs[3])")
+    ap.add_argument("--surgery", action="store_true", help="append the stage-1 feature extractor of train.py (SURVEY 8(f)4)")
     return ap.parse_args()
 
 
@@ -544,6 +545,67 @@ def text_leg(cfg, peaks):
             "similarity_hbm_frac": 64 * n_cls * HEAD_BYTES_IMG / (ms2 / 1e3) / 1e9 / peaks["hbm_gbs"]}
 
 
+def surgery_leg():
+    """stage 1 of train.py (lines 74-85, under no_grad) at its own defaults - 518 px, batch 2 (train.py:186,
+    199), DAPM_layer 20 - and at batch 8: surgery CLIP patch features at [6,12,18,24] + the plain CLIP's class feature.
+    Beside it the same op sequence in stock PyTorch on this GPU (the oracle's restatement, TF32 on and off)."""
+    import torch
+    orc = _oracle()
+    from aaclip_b200 import synth
+    from aaclip_b200.clip import CLIP
+    from aaclip_b200.surgery import CLIPImageEncoder, surgery_patch_features
+    cfg = synth.ModelCfg(image_size=518)
+    sd = synth.clip_state_dict(cfg, 0, text=False)
+    model = CLIP(cfg, text=False)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda()
+    sd = {k: v.cuda() for k, v in sd.items()}
+    levels = [6, 12, 18, 24]
+    enc = CLIPImageEncoder(model, levels, surgery_until_layer=20, max_batch=8)
+    plain = CLIPImageEncoder(model, [], max_batch=8)
+    out = {"workload": "train.py:74-85 at 518 px (1370 tokens), DAPM_layer 20: v-v attention over the batch in the last 19 "
+                       "blocks, 4 levels of projected patch features + the un-modified CLIP's class feature (2 ViT-L passes)",
+           "levels": levels}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def ev(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+
+    try:
+        for B in (2, 8):
+            img = synth.images(B, cfg, seed=3).cuda()
+            ms, feats = ev(lambda: surgery_patch_features(enc, plain, img), 10)
+            rec = {"ms_per_batch": ms, "images_per_s": B / (ms / 1e3)}
+
+            def ref():
+                with torch.no_grad():
+                    return orc.surgery_patch_features(sd, sd, img, levels=levels, surgery_until_layer=20)
+            for name, tf32 in (("torch_fp32_tf32_off", False), ("torch_fp32_tf32_on", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                rms, rf = ev(ref, 2)
+                rec[name] = {"ms_per_batch": rms, "images_per_s": B / (rms / 1e3), "speedup_of_this_path": rms / ms}
+                if not tf32:
+                    rec["parity_vs_torch_fp32"] = {
+                        "features_max_abs": max(float((a - b).abs().max()) for a, b in zip(feats, rf)),
+                        "min_cosine": min(float(torch.nn.functional.cosine_similarity(a, b, dim=-1).min()) for a, b in zip(feats, rf)),
+                        "tolerance": "features (two unit vectors added) <= 3e-2 max-abs, cosine >= 0.999"}
+            out[f"batch_{B}"] = rec
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del enc, plain, model, sd
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     out = _claim_stdout()
@@ -788,6 +850,7 @@ def main():
         lambda: torch_gpu_baseline(B, inputs, anchors, *eng.forward_fused(inputs[0], anchors, "Industrial")))
     leg("batch_sweep", args.sweep, lambda: sweep_leg(cfg, anchors, peaks))
     leg("text_path", args.text, lambda: text_leg(cfg, peaks))
+    leg("surgery_stage1", args.surgery, surgery_leg)
     if solo and "torch_gpu_baseline" in legs and "error" not in legs["torch_gpu_baseline"]:
         for k in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast"):
             legs["torch_gpu_baseline"][k]["speedup_of_this_path"] = value / legs["torch_gpu_baseline"][k]["images_per_s"]
@@ -824,6 +887,8 @@ def main():
             line["batch_sweep"] = legs["batch_sweep"]
         if "text_path" in legs:
             line["text_path"] = legs["text_path"]
+        if "surgery_stage1" in legs:
+            line["surgery_stage1"] = legs["surgery_stage1"]
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
