@@ -281,12 +281,29 @@ def torch_gpu_baseline(B: int, inputs, anchors, eng_maps, eng_scores):
             if name == "fp32_tf32_off" and eng_maps is not None:   # parity of the product against it, same run
                 mm = lambda x: (x - x.min()) / (x.max() - x.min())
                 ref_m, ref_s = run(inputs[0])
+                # ranking: pairs of images the engine orders differently from the fp32 run, and how far apart the fp32 run
+                # itself puts them (random-init weights give near-tied image scores: a swap inside the score tolerance is a
+                # tie, not a disagreement)
+                dr = ref_s[:, None] - ref_s[None, :]
+                de = eng_scores[:, None] - eng_scores[None, :]
+                disc = (dr * de) < 0
+                n_pairs = B * (B - 1) // 2
+                n_disc = int(disc.sum().item()) // 2
+                gap = float(dr.abs()[disc].max()) if n_disc else 0.0
+                nm = float((mm(eng_maps) - mm(ref_m)).abs().max())
+                se = float((eng_scores - ref_s).abs().max())
                 out["parity_vs_engine"] = {
-                    "normalised_map_max_abs": float((mm(eng_maps) - mm(ref_m)).abs().max()),
+                    "normalised_map_max_abs": nm,
                     "raw_map_max_abs": float((eng_maps - ref_m).abs().max()),
-                    "score_max_abs": float((eng_scores - ref_s).abs().max()),
+                    "score_max_abs": se,
+                    "score_spread_over_batch": float(ref_s.max() - ref_s.min()),
                     "ranking_identical": bool(torch.equal(eng_scores.argsort(), ref_s.argsort())),
-                    "tolerance": "normalised map <= 1e-2 (north star), identical ranking"}
+                    "ranking_kendall_tau": 1.0 - 2.0 * n_disc / max(n_pairs, 1),
+                    "discordant_pairs": n_disc, "pairs": n_pairs,
+                    "largest_reference_gap_of_a_discordant_pair": gap,
+                    "tolerance": "normalised map <= 1e-2 (north star); score <= 2e-3; ranking identical except ties: every "
+                                 "discordant pair lies within the score tolerance in the fp32 run itself",
+                    "pass": bool(nm <= 1e-2 and se <= 2e-3 and gap <= 2e-3)}
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
 
@@ -441,18 +458,25 @@ def drop_in_leg(B, cfg, inputs, anchors, steps):
             feats, det = model(x)
             return similarity_maps_summed(feats, anchors, cfg.image_size, "Industrial", det_feature=det)
 
+        # the two forms alternate call by call (each call bracketed by its own events): the step runs at the power cap, so
+        # a form timed second would be timed on a warmer GPU
+        forms = (("per_level_calls", ref_style), ("summed_call", one_call))
+        for i in range(2):
+            for _, fn in forms:
+                fn(inputs[i % len(inputs)])
+        torch.cuda.synchronize()
+        evs = {lname: [] for lname, _ in forms}
+        for i in range(steps):
+            for lname, fn in (forms if i % 2 == 0 else forms[::-1]):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(inputs[i % len(inputs)])
+                e1.record()
+                evs[lname].append((e0, e1))
+        torch.cuda.synchronize()
         leg = {}
-        for lname, fn in (("per_level_calls", ref_style), ("summed_call", one_call)):
-            for i in range(2):
-                fn(inputs[i % len(inputs)])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(steps):
-                fn(inputs[i % len(inputs)])
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / steps
+        for lname, _ in forms:
+            ms = sum(a.elapsed_time(b) for a, b in evs[lname]) / steps
             leg[lname] = {"ms_per_step": ms, "images_per_s": B / (ms / 1e3)}
         out[name] = leg
         model._engine.close()
