@@ -101,6 +101,7 @@ class AdaptedCLIP(nn.Module):
         )
         self._init_weights_()
         self._engine: Optional[Engine] = None
+        self._engine_sig = None
         self._versions: Dict[str, Tuple[int, int]] = {}
 
     def _init_weights_(self):
@@ -113,6 +114,10 @@ class AdaptedCLIP(nn.Module):
                 nn.init.xavier_uniform_(p)
 
     # ---------------------------------------------------------------------------------- engine plumbing
+    def _cfg_signature(self):
+        return (tuple(int(l) for l in self.levels), int(self.image_adapt_until), int(self.text_adapt_until), float(self.i_w),
+                float(self.t_w), bool(self.relu), int(self.max_batch))
+
     def _named_sources(self):
         for k, v in self.clipmodel.state_dict(keep_vars=True).items():
             yield "clip." + k, v
@@ -126,7 +131,14 @@ class AdaptedCLIP(nn.Module):
             raise RuntimeError("aaclip_b200.AdaptedCLIP runs on a B200 only (no CPU / PyTorch fallback); "
                                "move the model and its inputs to a cuda device")
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
-        if self._engine is None or self._engine.device != dev_index:
+        # the reference reads these attributes on every forward (model/adapter.py:90-101, 123-131): a change made after the
+        # first forward must take effect here too, so the context (and its cached graphs) is rebuilt when one differs
+        sig = self._cfg_signature()
+        if self._engine is not None and (self._engine.device != dev_index or self._engine_sig != sig):
+            self._engine.close()
+            self._engine = None
+        if self._engine is None:
+            self._engine_sig = sig
             cfg = _infer_cfg(self.clipmodel, list(self.levels), self.image_adapt_until, self.text_adapt_until, self.i_w,
                              self.t_w, self.relu)
             cfg.levels = effective_levels(self.levels, cfg.layers)

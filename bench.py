@@ -728,7 +728,13 @@ def main():
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
     t = torch.tensor([ms], device="cuda")
+    rank_ms = [ms / args.steps]
     if world > 1:
+        # every rank's own device time, for the record: the ranks never wait for each other inside the timed region, so
+        # the job's time (MAX over ranks) is the slowest GPU's, and single B200s differ by a few per cent at the power cap
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
@@ -904,6 +910,7 @@ def main():
             "cpu_baseline": legs.get("cpu_baseline"), "torch_gpu_baseline": legs.get("torch_gpu_baseline"),
             "drop_in": legs.get("drop_in"), "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
+            "rank_ms_per_step": [round(x, 3) for x in rank_ms],
             "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms),
                         "all": [round(x, 3) for x in step_ms]},
         }

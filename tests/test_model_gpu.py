@@ -748,3 +748,37 @@ def test_caller_side_stream_capture_joins_the_callers_graph(full):
             eng.forward_fused(img, T, out=out, extrema=ext)
         side.synchronize()
     assert torch.equal(out[0], maps_e)
+
+
+def test_attributes_changed_after_the_first_forward_take_effect():
+    """The reference reads `i_w`, `levels` and `image_adapt_until` on every forward (model/adapter.py:90-101): changing them
+    on a model that has already run must change the result exactly as a freshly built model would (the context and its
+    cached graphs are rebuilt)."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.adapter import AdaptedCLIP
+    from aaclip_b200.clip import CLIP
+    cfg = synth.ModelCfg(layers=4, t_layers=0, image_adapt_until=2, levels=[1, 2, 3, 4])
+    clip = CLIP(cfg, text=False)
+    sd, ia = synth.clip_state_dict(cfg, 3, text=False), synth.image_adapter_state_dict(cfg, 3)
+    clip.load_state_dict(sd, strict=False)
+    model = AdaptedCLIP(clip_model=clip, image_adapt_until=2, levels=[1, 2, 3, 4], relu=False, max_batch=2).to("cuda").eval()
+    model.image_adapter.load_state_dict(ia)
+    img = synth.images(2, cfg, seed=5)
+    T = synth.anchors(cfg, seed=2).cuda()
+    with torch.no_grad():
+        first, _ = model(img.cuda())
+        for _ in range(3):
+            model.predict(img.cuda(), T, "Industrial")          # primes the fused-forward graph cache
+        model.i_w = 0.3
+        model.levels = [4, 2]                                    # membership semantics: taps after blocks 2 and 4
+        seg, det = model(img.cuda())
+        maps, _ = model.predict(img.cuda(), T, "Industrial")
+        ia_sub = dict(ia)
+        seg_o, det_o = orc.visual_forward(sd, ia_sub, img, layers=4, image_adapt_until=2, image_adapt_weight=0.3, levels=(2, 4))
+        map_o, _ = orc.predict(seg_o, det_o, T.cpu(), 336, "Industrial")
+    assert len(seg) == 2
+    assert max((a.cpu() - b).abs().max().item() for a, b in zip(seg, seg_o)) < SEG_TOL
+    assert (det.cpu() - det_o).abs().max().item() < SEG_TOL
+    assert (_mm(maps.cpu()) - _mm(map_o)).abs().max().item() < MAP_NORM_TOL
+    assert (seg[0] - first[1]).abs().max().item() > 1e-3       # block 2's tap moved with the adapter weight
