@@ -74,6 +74,16 @@ class _Visual(nn.Module):
         self.transformer = _Transformer(w, cfg.layers, cfg.heads, cfg.mlp_width, cfg.quick_gelu)
         self.ln_post = nn.LayerNorm(w)
         self.proj = nn.Parameter(scale * torch.randn(w, cfg.embed_dim))
+        self.dpam_layer: Optional[int] = None
+
+    @torch.no_grad()
+    def DAPM_replace(self, DPAM_layer):
+        """model/transformer.py:406-425 (train.py:243): the last DPAM_layer - 1 blocks run the v-v `Attention` with their
+        own in_proj / out_proj weights.  The container keeps its parameter names; the engine switches kernels
+        (`CLIP.encode_image` below, aaclip_b200/surgery.py)."""
+        if DPAM_layer is not None and DPAM_layer - 1 > len(self.transformer.resblocks):
+            raise IndexError(f"DAPM_replace({DPAM_layer}): the tower has {len(self.transformer.resblocks)} blocks")
+        self.dpam_layer = DPAM_layer
 
 
 class CLIP(nn.Module):
@@ -97,8 +107,24 @@ class CLIP(nn.Module):
     def encode_text(self, text, normalize: bool = False):
         raise NotImplementedError("un-adapted CLIP.encode_text is outside the accelerated hot path (SURVEY 8)")
 
-    def encode_image(self, image, *a, **k):
-        raise NotImplementedError("un-adapted CLIP.encode_image is outside the accelerated hot path (SURVEY 8)")
+    def encode_image(self, image, out_layers, normalize: bool = False, max_batch: int = 8):
+        """model/model.py:185-188: (pooled [B, E], [tokens [B, L, width] after each block in out_layers]) on the CUDA
+        engine - what train.py:75-76 calls on the surgery model and on the un-modified one.  One engine context per
+        distinct set of out_layers (each holds the tower's weights); `visual.DAPM_replace` is honoured."""
+        from .adapter import effective_levels
+        from .surgery import CLIPImageEncoder
+        key = tuple(effective_levels(out_layers, len(self.visual.transformer.resblocks)))
+        encoders = self.__dict__.setdefault("_image_encoders", {})
+        enc = encoders.get(key)
+        if enc is None or enc.max_batch < image.shape[0]:
+            if enc is not None and enc._engine is not None:
+                enc._engine.close()
+            enc = CLIPImageEncoder(self, list(key), surgery_until_layer=self.visual.dpam_layer,
+                                   max_batch=max(max_batch, int(image.shape[0])))
+            encoders[key] = enc
+        if enc.surgery_until_layer != self.visual.dpam_layer:
+            enc.DAPM_replace(self.visual.dpam_layer)
+        return enc.encode_image(image.float().contiguous(), None, normalize)
 
 
 def create_model(model_name: str = "ViT-L-14-336", img_size: int = 336, pretrained: Optional[str] = None,

@@ -384,3 +384,5 @@ def test_surgery_encoder_refuses_cpu_inputs():
         enc.encode_image(torch.zeros(1, 3, 56, 56))
     with pytest.raises(RuntimeError, match="B200 only"):
         enc.patch_features(torch.zeros(1, 3, 56, 56))
+    with pytest.raises(RuntimeError, match="B200 only"):
+        CLIP(synth.tiny_cfg(), text=False).encode_image(torch.zeros(1, 3, 56, 56), [2, 4])

@@ -198,3 +198,39 @@ def test_vitl_surgery_vs_golden_from_the_real_reference():
         assert (got - ref).abs().max().item() <= 2 * FEAT_TOL, lvl
         cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1).min().item()
         assert cos >= 0.999, (lvl, cos)
+
+
+def test_train_py_lines_75_to_85_run_unchanged_on_the_container():
+    """The literal call sequence of train.py:75-85 (and :243) on aaclip_b200.clip.CLIP: `visual.DAPM_replace`,
+    `encode_image(image, out_layers)` on the surgery model and on the un-modified one, the rest in the caller's torch ops."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.clip import CLIP
+    cfg, sd, clip_surgery = _tiny_models()
+    clip_plain = CLIP(cfg, text=False)
+    clip_plain.load_state_dict(sd, strict=False)
+    clip_plain = clip_plain.cuda()
+    clip_surgery.visual.DAPM_replace(DPAM_layer=3)                                       # train.py:243
+    image = synth.images(2, cfg, seed=21).cuda()
+    levels = [1, 2, 4]
+    with torch.no_grad():
+        _, patch_features = clip_surgery.encode_image(image, levels)                      # :75
+        cls_token, _ = clip_plain.encode_image(image, [])                                 # :76
+        cls_token = cls_token / cls_token.norm(dim=-1, keepdim=True)                      # :77
+        patch_features = [clip_surgery.visual.ln_post(t[:, 1:, :]) for t in patch_features]   # :78-80
+        patch_features = [t @ clip_surgery.visual.proj for t in patch_features]           # :81
+        patch_features = [t / t.norm(dim=-1, keepdim=True) for t in patch_features]       # :82-84
+        patch_features = [t + cls_token.unsqueeze(1) for t in patch_features]             # :85
+        want = orc.surgery_patch_features(sd, sd, image.cpu(), levels=levels, surgery_until_layer=3, patch_size=cfg.patch_size,
+                                          heads=cfg.heads, layers=cfg.layers)
+    assert len(patch_features) == 3
+    for f, fo in zip(patch_features, want):
+        assert (f.cpu() - fo).abs().max().item() <= 2 * FEAT_TOL
+    # the un-modified model did not pick the surgery up, and switching it off again restores ordinary attention
+    with torch.no_grad():
+        _, plain_tokens = clip_plain.encode_image(image, levels)
+        clip_surgery.visual.DAPM_replace(None)
+        _, back = clip_surgery.encode_image(image, levels)
+    assert all(torch.equal(a, b) for a, b in zip(plain_tokens, back))
+    with pytest.raises(IndexError):
+        clip_surgery.visual.DAPM_replace(cfg.layers + 2)
