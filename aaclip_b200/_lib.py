@@ -80,6 +80,7 @@ SIGNATURES = {
     "aaclip_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "aaclip_attention_trace": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "aaclip_adapter_mix": (_i, [_vp, _vp, _f, _i, _i, _vp]),
+    "aaclip_set_text_final": (_i, [_vp, _i]),
     "aaclip_dapm_replace": (_i, [_vp, _i]),
     "aaclip_encode_image": (_i, [_vp, _vp, _i, C.POINTER(_vp), _vp, _i, _vp]),
     "aaclip_vv_attention": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -104,8 +104,49 @@ class CLIP(nn.Module):
             mask = torch.full((cfg.t_context, cfg.t_context), float("-inf")).triu_(1)
             self.register_buffer("attn_mask", mask, persistent=False)
 
-    def encode_text(self, text, normalize: bool = False):
-        raise NotImplementedError("un-adapted CLIP.encode_text is outside the accelerated hot path (SURVEY 8)")
+    def encode_text(self, text, normalize: bool = False, max_text: int = 256):
+        """The un-adapted `CLIP.encode_text` (model/model.py:190-200): token + positional embedding, the causal text
+        tower, ln_final, EOT row `@ text_projection`; int tokens [n, context] -> fp32 [n, embed_dim].  test.py:197-200 builds
+        the class anchors from it when no text adapter is used (`get_adapted_text_embedding(clip_model, ...)`).  Runs on a
+        text-only engine context (no adapters, plain final projection); parameters are re-uploaded when they change."""
+        import torch.nn.functional as F
+        from .engine import Engine
+        if not hasattr(self, "token_embedding"):
+            raise RuntimeError("this CLIP was built without a text tower (text=False)")
+        if not text.is_cuda:
+            raise RuntimeError("aaclip_b200.CLIP.encode_text runs on a B200 only (no CPU / PyTorch fallback)")
+        tw = self.token_embedding.weight.shape[1]
+        if tuple(self.text_projection.shape) != (tw, tw):
+            raise ValueError(f"text_projection {tuple(self.text_projection.shape)}: only square projections are supported")
+        dev = text.device.index if text.device.index is not None else torch.cuda.current_device()
+        st = self.__dict__.setdefault("_text_engine", {})
+        if st.get("engine") is None or st["engine"].device != dev:
+            blocks = self.transformer.resblocks
+            cfg = ModelCfg(image_size=14, patch_size=14, width=256, layers=1, heads=4, embed_dim=256, levels=[1],
+                           image_adapt_until=0, text_adapt_until=0, relu=False,
+                           quick_gelu=type(blocks[0].mlp.gelu).__name__ == "QuickGELU",
+                           t_context=self.positional_embedding.shape[0], t_vocab=self.token_embedding.weight.shape[0],
+                           t_width=tw, t_heads=blocks[0].attn.num_heads, t_layers=len(blocks))
+            st["engine"] = Engine(cfg, device=dev, max_batch=1, max_text=max_text, text=True)
+            st["engine"].set_text_final(leaky=False)
+            st["versions"] = {}
+        eng, versions = st["engine"], st["versions"]
+        dirty = False
+        for k, t in self.state_dict(keep_vars=True).items():
+            if k.startswith("visual."):
+                continue
+            key = "text_adapter.0.fc.0.weight" if k == "text_projection" else "clip." + k
+            if key not in eng._wmap:
+                continue
+            sig = (t.data_ptr(), t._version)
+            if versions.get(key) != sig:
+                eng.set_weight(key, t.detach().float().t().contiguous() if k == "text_projection" else t)
+                versions[key] = sig
+                dirty = True
+        if dirty:
+            torch.cuda.synchronize(dev)
+        out = eng.text_forward(text)
+        return F.normalize(out, dim=-1) if normalize else out
 
     def encode_image(self, image, out_layers, normalize: bool = False, max_batch: int = 8):
         """model/model.py:185-188: (pooled [B, E], [tokens [B, L, width] after each block in out_layers]) on the CUDA

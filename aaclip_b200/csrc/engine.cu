@@ -144,6 +144,7 @@ struct aaclip_ctx {
   Tower t;
   float *tok_emb = nullptr, *t_pos = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr;
   bf16* t_final = nullptr;
+  int t_final_act = gemm::ACT_LEAKY;   // aaclip_set_text_final: LEAKY = text_adapter[-1], NONE = CLIP's text_projection
   // workspaces
   int cap_rows = 0;  // rows of the token-major buffers
   float *x = nullptr, *a = nullptr, *s = nullptr, *dots = nullptr, *det = nullptr, *stage = nullptr, *rownorm = nullptr,
@@ -976,6 +977,16 @@ extern "C" int aaclip_forward_fused_host(aaclip_ctx* c, const float* host_image,
   return host::OK;
 }
 
+// What follows ln_final on the EOT row: leaky != 0 (default) - `text_adapter[-1]` = Linear + LeakyReLU (model/adapter.py:140);
+// leaky == 0 - a plain projection, i.e. `@ text_projection` of the un-adapted CLIP.encode_text (model/model.py:190-200) when
+// the final-projection slot holds text_projection^T and the context has no text adapters (text_adapt_until = 0).
+extern "C" int aaclip_set_text_final(aaclip_ctx* c, int leaky) {
+  TRY(check_ready(c));
+  if (c->cfg.t_layers <= 0) return host::fail(host::ERR_STATE, "set_text_final: context has no text tower");
+  c->t_final_act = leaky ? gemm::ACT_LEAKY : gemm::ACT_NONE;
+  return host::OK;
+}
+
 extern "C" int aaclip_text_forward(aaclip_ctx* c, const int32_t* tokens, int n, float* out, void* stream_) {
   TRY(check_ready(c));
   const aaclip_cfg& cfg = c->cfg;
@@ -997,7 +1008,7 @@ extern "C" int aaclip_text_forward(aaclip_ctx* c, const int32_t* tokens, int n, 
     eot_gather_kernel<<<nn, 256, 0, st>>>(tk, c->x, ctx, tw, c->a);
     AACLIP_CUDA_CHECK(cudaGetLastError()); c->launches++;
     RUN(PC_LAYERNORM, k::launch_layernorm(c->a, c->ln_final_g, c->ln_final_b, 1e-5f, nn, tw, 0, 0, 0, c->xn, nullptr, st));
-    RUN(PC_OTHER, k::launch_gemm(c->xn, tw, c->t_final, tw, nn, tw, tw, nullptr, out + (long long)n0 * tw, tw, gemm::ACT_LEAKY,
+    RUN(PC_OTHER, k::launch_gemm(c->xn, tw, c->t_final, tw, nn, tw, tw, nullptr, out + (long long)n0 * tw, tw, c->t_final_act,
                        gemm::OUT_F32, nullptr, 0, c->cta_group, st));
   }
   return host::OK;

@@ -173,6 +173,10 @@ class Engine:
                                              self._stream()))
         return seg, det
 
+    def set_text_final(self, leaky: bool) -> None:
+        """text_adapter[-1] (Linear + LeakyReLU, the default) or a plain projection (CLIP's text_projection) after ln_final."""
+        check(self.lib.aaclip_set_text_final(self._ctx, int(bool(leaky))))
+
     def dapm_replace(self, dpam_layer: Optional[int]) -> None:
         """VisionTransformer.DAPM_replace(DPAM_layer) (model/transformer.py:406-425): the last DPAM_layer - 1 visual
         blocks use the batch-coupled v-v attention (:123-152).  None / 0 / 1 restores ordinary attention."""

@@ -238,6 +238,11 @@ int aaclip_add_image_vector(float* tokens, const float* vec, int B, int P, int E
 /* ---- AdaptedCLIP.encode_text(adapt_text=True) (model/adapter.py:114-145) ---------------------------- */
 /* tokens int32 [n, context] (model/tokenizer.py:150-185); out fp32 [n, t_width], un-normalised. */
 int aaclip_text_forward(aaclip_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);
+/* What follows ln_final on the EOT row of aaclip_text_forward: leaky != 0 (default) - text_adapter[-1] = Linear + LeakyReLU
+ * (model/adapter.py:140); leaky == 0 - a plain projection: with text_projection^T in the final-projection slot and
+ * text_adapt_until = 0 the entry is the un-adapted CLIP.encode_text (model/model.py:190-200; test.py:197-200 builds the
+ * anchors from it when no text adapter is used). */
+int aaclip_set_text_final(aaclip_ctx* ctx, int leaky);
 
 /* forward_utils.py:155-161: emb fp32 [n, width] (encode_text output of one prompt state) -> rows L2-normalised,
  * averaged, re-normalised, written to column `col` (0 = normal, 1 = abnormal) of anchors fp32 [width, 2]. */

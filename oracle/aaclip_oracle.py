@@ -195,6 +195,21 @@ def encode_text(clip_sd: SD, text_adapter_sd: SD, tokens: torch.Tensor, *, heads
     return F.leaky_relu(F.linear(eot, text_adapter_sd[f"{text_adapt_until}.fc.0.weight"]), 0.01)
 
 
+def clip_encode_text(clip_sd: SD, tokens: torch.Tensor, *, heads: int = 12, layers: int = 12, quick_gelu: bool = False,
+                     normalize: bool = False) -> torch.Tensor:
+    """The un-adapted `CLIP.encode_text` (model/model.py:189-200; what `AdaptedCLIP.encode_text(adapt_text=False)` delegates to,
+    model/adapter.py:115-116, and what test.py:197-200 builds anchors from): tokens int [n, ctx] -> [n, embed_dim]."""
+    sd = clip_sd
+    x = F.embedding(tokens.long(), sd["token_embedding.weight"])               # :191
+    x = x + sd["positional_embedding"]                                         # :193
+    mask = causal_mask(tokens.shape[1]).to(x.device)
+    for i in range(layers):                                                    # :195
+        x = residual_attention_block(x, sd, f"transformer.resblocks.{i}.", heads, quick_gelu, mask)
+    x = layer_norm(x, sd, "ln_final.")                                         # :197
+    x = x[torch.arange(x.shape[0], device=x.device), tokens.argmax(dim=-1)] @ sd["text_projection"]   # :199
+    return F.normalize(x, dim=-1) if normalize else x                          # :200
+
+
 def class_text_anchor(emb_normal: torch.Tensor, emb_abnormal: torch.Tensor) -> torch.Tensor:
     """forward_utils.py:155-161: per-sentence L2 norm -> mean -> L2 norm, stacked to [width, 2]."""
     cols = []

@@ -162,6 +162,13 @@ def main():
             anchors_ref[cls] = ref_fu.get_adapted_single_class_text_embedding(model, "MVTec", cls, "cpu")
             a_o = orc.class_text_anchor(orc.encode_text(sd, ta, toks[0]), orc.encode_text(sd, ta, toks[1]))
             report[f"anchor_{cls}_maxdiff"] = maxdiff(anchors_ref[cls], a_o)
+    # the un-adapted text path (model/model.py:189-200; test.py:197-200 when no text adapter is used)
+    with torch.no_grad():
+        plain_ref = model.clipmodel.encode_text(tok_synth)
+        plain_o = orc.clip_encode_text(sd, tok_synth)
+        assert torch.equal(model.encode_text(tok_synth, adapt_text=False), plain_ref)   # model/adapter.py:115-116
+    report["text_plain_maxdiff"] = maxdiff(plain_ref, plain_o)
+    torch.save({"tok_synth_seed": 2, "emb_plain": plain_ref.clone()}, os.path.join(out_dir, "text_plain_vitl336.pt"))
     torch.save({"tok_synth_seed": 2, "emb_synth": emb_ref.clone(),
                 "prompt_tokens": prompts, "anchors": anchors_ref,
                 "class_names_mvtec": list(CLASS_NAMES["MVTec"])},

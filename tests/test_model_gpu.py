@@ -782,3 +782,38 @@ def test_attributes_changed_after_the_first_forward_take_effect():
     assert (det.cpu() - det_o).abs().max().item() < SEG_TOL
     assert (_mm(maps.cpu()) - _mm(map_o)).abs().max().item() < MAP_NORM_TOL
     assert (seg[0] - first[1]).abs().max().item() > 1e-3       # block 2's tap moved with the adapter weight
+
+
+def test_plain_clip_encode_text_vs_golden_and_anchor_path():
+    """`CLIP.encode_text` of the container = the un-adapted text path (model/model.py:189-200; what
+    `AdaptedCLIP.encode_text(adapt_text=False)` delegates to and what test.py:197-200 builds anchors from), on a text-only
+    engine context: against the golden of the real reference, normalised form, re-upload on a changed parameter."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.adapter import AdaptedCLIP
+    from aaclip_b200.clip import CLIP
+    cfg = synth.VIT_L_14_336
+    g = _load("text_plain_vitl336.pt")
+    sd = synth.clip_state_dict(cfg, 0)
+    clip = CLIP(cfg)
+    clip.load_state_dict(sd, strict=True)
+    clip = clip.cuda()
+    tok = synth.tokens(6, cfg, seed=g["tok_synth_seed"]).cuda()
+    emb = clip.encode_text(tok)
+    torch.cuda.synchronize()
+    ref = g["emb_plain"]
+    rel = ((emb.cpu() - ref).abs().max() / ref.abs().max()).item()
+    print(f"[plain text emb] rel_to_max err = {rel:.3e}")
+    assert tuple(emb.shape) == (6, 768) and rel < 2e-2
+    n = clip.encode_text(tok, normalize=True)
+    assert (n.norm(dim=-1) - 1).abs().max().item() < 1e-5
+    # AdaptedCLIP.encode_text(adapt_text=False) delegates to it (model/adapter.py:115-116)
+    model = AdaptedCLIP(clip_model=clip, relu=False).to("cuda").eval()
+    assert torch.equal(model.encode_text(tok, adapt_text=False), emb)
+    # a changed parameter is picked up
+    with torch.no_grad():
+        clip.text_projection.mul_(0.5)
+        half = clip.encode_text(tok)
+    assert (half - 0.5 * emb).abs().max().item() <= 2e-2 * emb.abs().max().item()
+    with pytest.raises(RuntimeError, match="B200 only"):
+        clip.encode_text(tok.cpu())

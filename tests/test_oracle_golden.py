@@ -137,3 +137,13 @@ def test_vv_attention_properties():
     assert (out[:1] - one).abs().max() > 1e-3
     perm = torch.tensor([2, 0, 3, 1])
     assert torch.allclose(orc.vv_attention(x[perm], sd, "a.", heads), out[perm], atol=1e-5)
+
+
+def test_plain_clip_encode_text_vs_reference_golden(weights):
+    """The un-adapted CLIP.encode_text (model/model.py:189-200) of the real reference vs the restatement."""
+    cfg, sd, _, _ = weights
+    g = _load("text_plain_vitl336.pt")
+    with torch.no_grad():
+        emb = orc.clip_encode_text(sd, synth.tokens(6, cfg, seed=g["tok_synth_seed"]))
+    assert emb.shape == g["emb_plain"].shape == (6, 768)
+    assert (emb - g["emb_plain"]).abs().max() < TOL * g["emb_plain"].abs().max().clamp_min(1.0)
