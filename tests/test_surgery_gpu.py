@@ -234,3 +234,29 @@ def test_train_py_lines_75_to_85_run_unchanged_on_the_container():
     assert all(torch.equal(a, b) for a, b in zip(plain_tokens, back))
     with pytest.raises(IndexError):
         clip_surgery.visual.DAPM_replace(cfg.layers + 2)
+
+
+def test_vitl_surgery_at_train_py_defaults_518px_batch_2_vs_oracle():
+    """train.py's own operating point (--img_size 518, --image_batch_size 2, --surgery_until_layer 20; train.py:186-199):
+    1370 tokens per image, v-v attention over a batch of two in the last 19 blocks, against the oracle on the host."""
+    import aaclip_oracle as orc
+    from aaclip_b200 import synth
+    from aaclip_b200.clip import CLIP
+    from aaclip_b200.surgery import CLIPImageEncoder, surgery_patch_features
+    cfg = synth.ModelCfg(image_size=518)
+    sd = synth.clip_state_dict(cfg, 0, text=False)
+    model = CLIP(cfg, text=False)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda()
+    levels = [6, 12, 18, 24]
+    enc = CLIPImageEncoder(model, levels, surgery_until_layer=20, max_batch=2)
+    plain = CLIPImageEncoder(model, [], max_batch=2)
+    img = synth.images(2, cfg, seed=6)
+    feats = surgery_patch_features(enc, plain, img.cuda())
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = orc.surgery_patch_features(sd, sd, img, levels=levels, surgery_until_layer=20)
+    for lvl, (f, fo) in enumerate(zip(feats, want)):
+        assert tuple(f.shape) == (2, 37 * 37, 768)
+        assert (f.cpu() - fo).abs().max().item() <= 2 * FEAT_TOL, lvl
+        assert torch.nn.functional.cosine_similarity(f.cpu(), fo, dim=-1).min().item() >= 0.999, lvl
