@@ -10,9 +10,10 @@
 // result of an image depends on the other images of its batch, so a batch is never split into chunks.
 //
 // Work is tiny next to the GEMMs (L * heads * batch^2 * 64 * 4 flop; train.py runs batch 2): one warp per
-// (token, head) item, the item's `batch` value rows staged in shared memory as fp32 (row pitch 65 floats: a lane
-// reads its own query row without bank conflicts, a key row is a broadcast), lane = query image, two passes over the
-// keys (row maximum, then exponentials and the weighted sum).  Rows are 128-byte bf16 segments of the GEMM output.
+// (token, head) item.  Batches of up to 8 images: lane = two channels, dot products by warp shuffles, no shared memory
+// (vv_attention_small_kernel).  Larger batches: the item's value rows staged in shared memory as fp32 (row pitch 65
+// floats: a lane reads its own query row without bank conflicts, a key row is a broadcast), lane = query image, two passes
+// over the keys (row maximum, then exponentials and the weighted sum).  Rows are 128-byte bf16 segments of the GEMM output.
 #include <stdarg.h>
 #include <algorithm>
 #include "common.cuh"
@@ -94,6 +95,68 @@ vv_attention_kernel(const bf16* __restrict__ v, int ldv, bf16* __restrict__ out,
   }
 }
 
+// Small batches (train.py runs 2): the lane-per-query form above leaves 30 of 32 lanes idle and walks 64-long dependent
+// FMA chains out of shared memory - 49 us per launch at B = 2, L = 1370.  Here a lane owns two CHANNELS of every image's
+// value row (the bf16x2 it loads, one coalesced 128-byte row per image), the NB (NB + 1) / 2 distinct dot products (the
+// score matrix is symmetric) are summed over the warp by butterfly shuffles, every lane evaluates the NB x NB softmax,
+// and writes its two channels of the NB output rows.  No shared memory, ~40 registers.
+constexpr int VV_SMALL_MAX = 8;
+constexpr int VV_SMALL_WARPS = 8;
+
+template <int NB>
+__global__ void __launch_bounds__(VV_SMALL_WARPS * 32)
+vv_attention_small_kernel(const bf16* __restrict__ v, int ldv, bf16* __restrict__ out, int ldo, int L, int heads,
+                          float scale_log2e) {
+  ptx::grid_dep_sync();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long items = (long long)L * heads;
+  for (long long item = (long long)blockIdx.x * VV_SMALL_WARPS + warp; item < items;
+       item += (long long)gridDim.x * VV_SMALL_WARPS) {
+    const int l = int(item / heads), h = int(item % heads);
+    float2 x[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      x[b] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + ((size_t)b * L + l) * ldv + h * VV_D + 2 * lane));
+    float s[NB][NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int c = b; c < NB; ++c) {
+        float d = fmaf(x[b].x, x[c].x, x[b].y * x[c].y);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        s[b][c] = d;
+        s[c][b] = d;
+      }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float m = s[b][0];
+#pragma unroll
+      for (int c = 1; c < NB; ++c) m = fmaxf(m, s[b][c]);
+      float sum = 0.f, ox = 0.f, oy = 0.f;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        const float p = exp2f((s[b][c] - m) * scale_log2e);
+        sum += p;
+        ox = fmaf(p, x[c].x, ox);
+        oy = fmaf(p, x[c].y, oy);
+      }
+      const float inv = 1.f / sum;
+      *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * L + l) * ldo + h * VV_D + 2 * lane) =
+          __floats2bfloat162_rn(ox * inv, oy * inv);
+    }
+  }
+}
+
+template <int NB>
+cudaError_t launch_small(const bf16* v, int ldv, bf16* out, int ldo, int L, int heads, int sms, cudaStream_t stream) {
+  const long long items = (long long)L * heads;
+  const long long want = (items + VV_SMALL_WARPS - 1) / VV_SMALL_WARPS;
+  const int grid = (int)std::min<long long>(want, 8LL * sms);
+  return host::launch(vv_attention_small_kernel<NB>, dim3(grid), dim3(VV_SMALL_WARPS * 32), 0, stream, v, ldv, out, ldo, L, heads,
+                      0.125f * 1.4426950408889634f);
+}
+
 }  // namespace
 
 int k::vv_attention_max_batch() { return VV_MAX_BATCH; }
@@ -107,9 +170,20 @@ int k::launch_vv_attention(const void* v, int ldv, void* out, int ldo, int B, in
   if (ldv % 8 != 0 || ldo % 8 != 0 || ldv < heads * VV_D || ldo < heads * VV_D ||
       (reinterpret_cast<uintptr_t>(v) & 15u) != 0 || (reinterpret_cast<uintptr_t>(out) & 15u) != 0)
     return host::fail(host::ERR_INVALID, "vv_attention: rows must be 16-byte aligned and hold heads * 64 values");
-  const size_t smem = (size_t)VV_WARPS * B * VV_PITCH * sizeof(float);
   int dev = 0;
   AACLIP_CUDA_CHECK(cudaGetDevice(&dev));
+  if (B <= VV_SMALL_MAX) {
+    const int sm = host::sm_count(dev) > 0 ? host::sm_count(dev) : 148;
+    const bf16* vp = static_cast<const bf16*>(v);
+    bf16* op = static_cast<bf16*>(out);
+    switch (B) {
+#define VV_CASE(N_) case N_: AACLIP_CUDA_CHECK(launch_small<N_>(vp, ldv, op, ldo, L, heads, sm, stream)); break;
+      VV_CASE(1) VV_CASE(2) VV_CASE(3) VV_CASE(4) VV_CASE(5) VV_CASE(6) VV_CASE(7) VV_CASE(8)
+#undef VV_CASE
+    }
+    return host::OK;
+  }
+  const size_t smem = (size_t)VV_WARPS * B * VV_PITCH * sizeof(float);
   // the > 48 KB dynamic-smem opt-in is per (kernel, device): remembered per device
   static bool configured[64] = {false};
   if (smem > 48 * 1024 && !(dev >= 0 && dev < 64 && configured[dev])) {

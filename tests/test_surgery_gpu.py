@@ -28,7 +28,7 @@ def _vv_ref(v, B, L, heads):
     return (a @ x).permute(2, 0, 1, 3).reshape(B * L, heads * 64)
 
 
-@pytest.mark.parametrize("B", [1, 2, 3, 8, 33, 64, 128])
+@pytest.mark.parametrize("B", [1, 2, 3, 5, 8, 9, 33, 64, 128])
 def test_vv_attention_kernel_vs_formula(B):
     from aaclip_b200 import ops
     L, heads = (577, 16) if B <= 3 else (29, 16)
