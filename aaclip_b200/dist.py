@@ -24,36 +24,51 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 
 def gather_scores(local: torch.Tensor, total: int, group: Optional[dist.ProcessGroup] = None,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """All-gather per-image scores of a sharded batch into one [total] tensor on every rank.
+    """All-gather per-image values of a sharded batch into one [total, ...] tensor on every rank.
 
-    `local` holds this rank's shard_range(total, rank, world) scores.  Even shards (total % world == 0, what the
-    benchmark and any fixed-batch loop use) are ONE collective straight into `out` (a preallocated [total] tensor;
-    allocated here when not given) - no padding, no concatenation, no extra kernels on the step.  Uneven shards are
-    padded to the largest shard so that a single fixed-size all_gather (NCCL on GPUs, gloo in the CPU tests) suffices.
+    `local` holds this rank's shard_range(total, rank, world) rows: scores [n], or any [n, ...] per-image record (the
+    (min, max) map extrema [n, 2]).  Even shards (total % world == 0, what the benchmark and any fixed-batch loop use)
+    are ONE collective straight into `out` (a preallocated [total, ...] tensor; allocated here when not given) - no
+    padding, no concatenation, no extra kernels on the step.  Uneven shards are padded to the largest shard so that a
+    single fixed-size all_gather (NCCL on GPUs, gloo in the CPU tests) suffices.
     """
+    tail = tuple(local.shape[1:])
     if not dist.is_available() or not dist.is_initialized():
-        if local.numel() != total:
+        if local.shape[0] != total:
             raise ValueError("single-process gather needs the full batch")
         return local
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     b, e = shard_range(total, rank, world)
-    if local.numel() != e - b:
-        raise ValueError(f"rank {rank} holds {local.numel()} scores, expected {e - b}")
+    if local.shape[0] != e - b:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} rows, expected {e - b}")
     if total % world == 0:
         if out is None:
-            out = torch.empty(total, dtype=local.dtype, device=local.device)
-        elif out.numel() != total or out.dtype != local.dtype or out.device != local.device or not out.is_contiguous():
-            raise ValueError("out must be a contiguous [total] tensor of local's dtype on local's device")
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+            out = torch.empty((total,) + tail, dtype=local.dtype, device=local.device)
+        elif (tuple(out.shape) != (total,) + tail or out.dtype != local.dtype or out.device != local.device
+              or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous [total, ...] tensor of local's dtype on local's device")
+        dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
         return out
     width = -(-total // world)
-    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded = torch.zeros((width,) + tail, dtype=local.dtype, device=local.device)
     padded[: e - b] = local
-    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
+    buf = torch.empty((world * width,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf.view(-1), padded.view(-1), group=group)
     parts = []
     for r in range(world):
         rb, re_ = shard_range(total, r, world)
-        parts.append(out[r * width: r * width + (re_ - rb)])
+        parts.append(buf[r * width: r * width + (re_ - rb)])
     return torch.cat(parts)
+
+
+def gather_extrema(local: torch.Tensor, total: int, group: Optional[dist.ProcessGroup] = None,
+                   out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The optional second collective of SURVEY 8(e): per-image map extrema (min, max) [n, 2] of this rank's shard ->
+    ([total, 2] on every rank, the global (min, max) [2]).  `metrics_eval` normalises the maps of a whole class set by its
+    global minimum and maximum and takes each image's normalised maximum (forward_utils.py:241-254): with the extrema of
+    every image on every rank that needs no pixel to leave the GPU that produced it."""
+    if local.dim() != 2 or local.shape[1] != 2:
+        raise ValueError("extrema must be [n, 2] (min, max) per image")
+    allx = gather_scores(local, total, group, out)
+    return allx, torch.stack([allx[:, 0].min(), allx[:, 1].max()])

@@ -136,6 +136,11 @@ def _gloo_worker(rank, world, total, port, q):
     if total % world == 0:   # even shards: one collective straight into a caller-owned buffer
         buf = torch.empty(total)
         ok = ok and gather_scores(full[b:e].clone(), total, out=buf) is buf and bool(torch.equal(buf, full))
+    # per-image records ride the same collective: the map extrema [n, 2] and their global (min, max)
+    from aaclip_b200.dist import gather_extrema
+    ex_full = torch.stack([full - 3.0, full * 2.0], 1)
+    allx, glob = gather_extrema(ex_full[b:e].clone(), total)
+    ok = ok and bool(torch.equal(allx, ex_full)) and bool(torch.equal(glob, torch.stack([ex_full[:, 0].min(), ex_full[:, 1].max()])))
     q.put((rank, ok))
     dist.barrier()
     dist.destroy_process_group()
