@@ -166,6 +166,11 @@ def test_surgery_context_never_splits_a_batch_and_validates_depth():
     enc.DAPM_replace(None)                       # ordinary attention: chunks of max_batch are fine again
     pooled, toks = enc.encode_image(img)
     assert tuple(toks[0].shape) == (3, cfg.tokens, cfg.width)
+    whole = CLIPImageEncoder(model, [4], max_batch=4)            # the same batch in one chunk: images are independent again
+    pooled_w, toks_w = whole.encode_image(img)
+    assert torch.equal(pooled, pooled_w) and torch.equal(toks[0], toks_w[0])
+    feats, feats_w = enc.patch_features(img), whole.patch_features(img)
+    assert torch.equal(feats[0], feats_w[0])
     with pytest.raises(RuntimeError, match="reaches past"):
         enc.DAPM_replace(cfg.layers + 2)         # the reference indexes resblocks[-i] out of range here
 
