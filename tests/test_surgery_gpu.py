@@ -171,6 +171,11 @@ def test_surgery_context_never_splits_a_batch_and_validates_depth():
     assert torch.equal(pooled, pooled_w) and torch.equal(toks[0], toks_w[0])
     feats, feats_w = enc.patch_features(img), whole.patch_features(img)
     assert torch.equal(feats[0], feats_w[0])
+    p0, t0 = whole.encode_image(img[:0].contiguous())             # an empty batch passes through
+    assert tuple(p0.shape) == (0, cfg.embed_dim) and tuple(t0[0].shape) == (0, cfg.tokens, cfg.width)
+    whole.DAPM_replace(3)
+    p0, t0 = whole.encode_image(img[:0].contiguous())
+    assert tuple(p0.shape) == (0, cfg.embed_dim) and tuple(t0[0].shape) == (0, cfg.tokens, cfg.width)
     with pytest.raises(RuntimeError, match="reaches past"):
         enc.DAPM_replace(cfg.layers + 2)         # the reference indexes resblocks[-i] out of range here
 
