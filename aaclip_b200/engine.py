@@ -3,7 +3,7 @@ reference-keyed state dicts, and the forward entry points.  Pure plumbing: point
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import torch
 
